@@ -1,0 +1,2 @@
+class LinearOperator:  # annotation only
+    pass
