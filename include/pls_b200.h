@@ -1,0 +1,187 @@
+/*
+ * pls_b200.h -- C ABI of the B200-native Projected Langevin Sampling (PLS) hot path.
+ *
+ * One shared library, libpls_b200.so (built from projected_langevin_sampling_b200/csrc/ by
+ * __graft_entry__.build()).  Plain pointers and sizes only: no torch types, no C++ in the signatures.
+ *
+ * The reference (jswu18/projected-langevin-sampling) is pure Python and has no FFI layer; the boundary a
+ * maintainer would bind is its Python class API.  Each entry point below names the reference method whose body
+ * it replaces (paths relative to the reference root, `pls/` = src/projected_langevin_sampling/).  The host-side
+ * mirror of that API that calls these functions lives in projected_langevin_sampling_b200/ (ctypes).
+ *
+ * Conventions
+ *   - every matrix is row-major float64 in DEVICE memory, described by (pointer, leading dimension in elements);
+ *   - N training points, M inducing points, M_k kept eigen-directions, J particles, D input dimension;
+ *   - all work is enqueued on the caller's stream (`stream` = cudaStream_t passed as void*); nothing synchronises
+ *     unless stated; buffers are caller-owned, the library allocates nothing on the device;
+ *   - every function returns 0 on success, non-zero otherwise (message via pls_last_error); nothing throws,
+ *     nothing exits;
+ *   - entry points are not re-entrant on the same ctx.
+ *
+ * Layout "augmented points" (built once by pls_prepare_points_f64): a point set (n x D) is stored as n rows of
+ * SP = pls_point_stride(D) doubles: [ (x_d - centre_d) / lengthscale_d  (D) | c | 1 | 0 ... ] with
+ * c = -0.5 * |scaled x|^2 (+ log outputscale for the inducing set), so that one dot product of a row-side vector
+ * with a column-side vector whose c/1 entries are swapped is the exponent of the RBF/ARD x Scale kernel.  For the
+ * linear (test-double) kernel the row is [x | 0 | 0 | 0 ...] and the Gram entry is the dot product itself.
+ */
+#ifndef PLS_B200_H_
+#define PLS_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PLS_ABI_VERSION 1
+
+/* base kernel k(x, x') -- pls/kernel.py:21-29 `.base_kernel`; gpytorch ScaleKernel(RBFKernel(ard_num_dims=D)) at the
+ * reference call sites pls/basis/orthonormal.py:36-41, src/inducing_point_selectors/conditional_variance.py:66-89;
+ * LINEAR is the reference's test double mockers/kernel.py:8-23. */
+enum { PLS_KERNEL_RBF = 0, PLS_KERNEL_LINEAR = 1 };
+
+/* costs -- pls/costs/{gaussian,bernoulli,poisson,multimodal,student_t}.py */
+enum { PLS_COST_GAUSSIAN = 0, PLS_COST_BERNOULLI = 1, PLS_COST_POISSON = 2, PLS_COST_MULTIMODAL = 3, PLS_COST_STUDENT_T = 4 };
+/* link functions -- pls/link_functions.py:30-80 */
+enum { PLS_LINK_IDENTITY = 0, PLS_LINK_SIGMOID = 1, PLS_LINK_PROBIT = 2, PLS_LINK_SQUARE = 3 };
+/* what pls_forward_f64 writes */
+enum {
+  PLS_EPI_PREDICTION = 0,      /* F = k(X,Z) W                      (n x J)        orthonormal.py:98-108            */
+  PLS_EPI_COST_DERIVATIVE = 1, /* d_2 c(y, F)                       (n x J)        PLS.calculate_cost_derivative    */
+  PLS_EPI_COST = 2             /* per 128-row tile: sum_n c(y_n,F)  (tiles x J)    PLS.calculate_cost               */
+};
+/* Langevin noise source for pls_project_update_f64 */
+enum {
+  PLS_NOISE_NONE = 0,   /* xi = 0 (deterministic drift only; used by tests)                                       */
+  PLS_NOISE_GIVEN = 1,  /* xi read from a caller buffer (parity mode: the reference's torch.normal stream)        */
+  PLS_NOISE_PHILOX = 2  /* xi = Philox4x32-10 + Box-Muller keyed on (seed, step, global row, global particle)     */
+};
+
+typedef struct pls_ctx pls_ctx;
+
+/* A likelihood cost with its link function.
+ *   closed_form != 0 selects the reference's hand-written derivative where it has one (gaussian/identity
+ *   gaussian.py:75-88, bernoulli/sigmoid bernoulli.py:64-77, poisson/square poisson.py:68-82, student_t/identity
+ *   student_t.py:74-88); otherwise the derivative is the chain rule (d cost/d mu) * link'(F), i.e. what the
+ *   reference's autograd fallback costs/base.py:68-84 evaluates (multimodal.py:79-91 is autograd-only).
+ *   observation_noise: gaussian = variance (gaussian.py:71,86); multimodal = std, squared inside (multimodal.py:56).
+ *   probit_divisor: the value the reference divides by inside erf (link_functions.py:42: sqrt(tensor(2.0)) in the
+ *   default dtype at call time). */
+typedef struct pls_cost {
+  int32_t cost_id;
+  int32_t link_id;
+  int32_t closed_form;
+  int32_t reserved;
+  double observation_noise;
+  double shift;
+  double bernoulli_noise;
+  double degrees_of_freedom;
+  double scale;
+  double link_jitter;
+  double probit_divisor;
+} pls_cost;
+
+/* ---- context ------------------------------------------------------------------------------------------------ */
+int pls_abi_version(void);
+int pls_ctx_create(int device, pls_ctx** ctx);
+void pls_ctx_destroy(pls_ctx* ctx);
+/* last error message of `ctx` (or of the failed pls_ctx_create when ctx == NULL); never NULL */
+const char* pls_last_error(const pls_ctx* ctx);
+/* number of SMs of the ctx device (grids are sized from it) */
+int pls_sm_count(const pls_ctx* ctx);
+
+/* ---- layout helpers (host only, no device work) --------------------------------------------------------------- */
+/* SP: doubles per augmented point row for input dimension d (d >= 1; returns -1 if d is unsupported) */
+int pls_point_stride(int d);
+/* number of N-splits pls_backward_f64 wants for an (m x j) gradient reduced over n_rows training rows */
+int pls_backward_splits(const pls_ctx* ctx, int64_t n_rows, int64_t m, int64_t j);
+
+/* ---- one-time setup ------------------------------------------------------------------------------------------ */
+/* Builds the augmented layout of a point set.  x: n x d (ldx).  inv_lengthscale, centre: HOST arrays of d doubles
+ * (ignored for PLS_KERNEL_LINEAR).  c_extra is added to the c entry (log(outputscale) for the inducing set, 0 for
+ * the training set).  out: n x pls_point_stride(d).
+ * Replaces the `x.div(lengthscale)` + centring + norm padding of the gpytorch kernel call in
+ * pls/basis/orthonormal.py:36-41. */
+int pls_prepare_points_f64(pls_ctx* ctx, int kernel_id, const double* x, int64_t n, int d, int64_t ldx,
+                           const double* inv_lengthscale, const double* centre, double c_extra, double* out,
+                           void* stream);
+/* Dense Gram out[i][j] = k(rows_i, cols_j) from two augmented sets (setup K_zz for the eigendecomposition,
+ * pls/basis/orthonormal.py:36-38,46-48; k(x*, Z) at predict time, orthonormal.py:232-235). */
+int pls_gram_f64(pls_ctx* ctx, int kernel_id, const double* rows_aug, int64_t n_rows, const double* cols_aug,
+                 int64_t n_cols, int d, double* out, int64_t ldo, void* stream);
+
+/* ---- the Langevin step, piece by piece ------------------------------------------------------------------------ */
+/* C (rows x j) = op(A) * B, op(A) = A (rows x k, lda) or A^T (A is k x rows, lda) when trans_a != 0.
+ * Used for W = V~ P (pls/basis/orthonormal.py:106-108, re-associated) and wherever a small dense product is needed. */
+int pls_gemm_f64(pls_ctx* ctx, int trans_a, const double* a, int64_t lda, const double* b, int64_t ldb, double* c,
+                 int64_t ldc, int64_t rows, int64_t j, int64_t k, void* stream);
+
+/* Forward contraction with on-the-fly Gram tiles: for training rows [0, n) of xa,
+ *   F[n][j] = sum_m k(x_n, z_m) W[m][j],      W = V~ P  (m x j, ldw, ldw even, 16-byte aligned)
+ * and the epilogue selected by `epilogue`.  y (n doubles) and cost are read for the cost epilogues only.
+ * out: n x j (ldo) for PREDICTION / COST_DERIVATIVE (ldo even, 16-byte aligned), ceil(n/128) x j (ldo) for COST.
+ * Replaces OrthonormalBasis.calculate_untransformed_train_prediction_samples (pls/basis/orthonormal.py:98-108) fused
+ * with <Cost>.calculate_cost_derivative / calculate_cost (pls/costs/*.py); the N x M Gram is never materialised. */
+int pls_forward_f64(pls_ctx* ctx, int kernel_id, const double* xa, int64_t n, const double* za, int64_t m, int d,
+                    const double* w, int64_t ldw, int64_t j, int epilogue, const pls_cost* cost, const double* y,
+                    double* out, int64_t ldo, void* stream);
+
+/* Back-projection with on-the-fly Gram tiles, split `splits` ways over the training rows [0, n) of xa:
+ *   gp[s][m][j] (+)= sum_{n in split s} k(z_m, x_n) dc[n][j]
+ * dc: n x j (lddc even, 16-byte aligned).  gp: splits x m x ldg.  accumulate != 0 adds to gp instead of overwriting
+ * (used when the training set is processed in row chunks).
+ * Replaces the `k(Z,X) @ cost_derivative` product of OrthonormalBasis._calculate_particle_update
+ * (pls/basis/orthonormal.py:151-155). */
+int pls_backward_f64(pls_ctx* ctx, int kernel_id, const double* za, int64_t m, const double* xa, int64_t n, int d,
+                     const double* dc, int64_t lddc, int64_t j, double* gp, int64_t ldg, int splits, int accumulate,
+                     void* stream);
+
+/* out[r][c] = sum_s gp[s][r][c] in increasing s (deterministic). */
+int pls_reduce_splits_f64(pls_ctx* ctx, const double* gp, int splits, int64_t rows, int64_t j, int64_t ldg,
+                          double* out, int64_t ldo, void* stream);
+
+/* delta = -eta * V~^T gm - eta * diag(inv_lambda) P + sqrt(2 eta) xi      (pls/basis/orthonormal.py:151-158)
+ * vt: M x M_k (ldv) scaled eigenvectors; gm: M x J (ldg) = k(Z,X) dc; p: M_k x J (ldp).
+ * in_place == 0: out (M_k x J, ldo) = delta  (PLS.calculate_particle_update, pls/projected_langevin_sampling.py:107-123)
+ * in_place != 0: out must alias p; p += delta  (the caller's `particles += particle_update`,
+ *                experiments/trainers.py:153-157).
+ * noise_mode GIVEN reads xi (M_k x J, ldxi) -- the reference's draw, src/samplers.py:30-35 via orthonormal.py:141-145;
+ * PHILOX generates xi[r][c] from (seed, step, r, j_global_offset + c), independent of how J is sharded. */
+int pls_project_update_f64(pls_ctx* ctx, const double* vt, int64_t ldv, int64_t m, int64_t m_k, const double* gm,
+                           int64_t ldg, const double* p, int64_t ldp, int64_t j, const double* inv_lambda, double eta,
+                           int noise_mode, const double* xi, int64_t ldxi, uint64_t seed, uint64_t step,
+                           int64_t j_global_offset, int in_place, double* out, int64_t ldo, void* stream);
+
+/* Elementwise d_2 c(y, F) on a caller-provided F (n x j): <Cost>.calculate_cost_derivative, pls/costs/*.py. */
+int pls_cost_derivative_f64(pls_ctx* ctx, const pls_cost* cost, const double* y, const double* f, int64_t ldf,
+                            int64_t n, int64_t j, double* out, int64_t ldo, void* stream);
+/* out[j] = sum_n c(y_n, F[n][j]): <Cost>.calculate_cost, pls/costs/*.py.  partial: workspace of
+ * ceil(n/128) x j doubles. */
+int pls_cost_value_f64(pls_ctx* ctx, const pls_cost* cost, const double* y, const double* f, int64_t ldf, int64_t n,
+                       int64_t j, double* partial, double* out, void* stream);
+/* out[c] = sum_t partial[t][c] (+ 0.5 * sum_r p[r][c]^2 * inv_lambda[r] when p != NULL): the per-particle energy of
+ * OrthonormalBasis.calculate_energy_potential (pls/basis/orthonormal.py:110-126) before the mean. */
+int pls_energy_terms_f64(pls_ctx* ctx, const double* partial, int64_t tiles, int64_t ldpart, const double* p,
+                         int64_t ldp, int64_t m_k, const double* inv_lambda, int64_t j, double* out, void* stream);
+/* Standard-normal Philox stream exactly as pls_project_update_f64 generates it (for tests and for callers that
+ * want the noise explicitly). */
+int pls_philox_normal_f64(pls_ctx* ctx, uint64_t seed, uint64_t step, int64_t rows, int64_t j,
+                          int64_t j_global_offset, double* out, int64_t ldo, void* stream);
+
+/* ---- ConditionalVariance inducing-point selector ------------------------------------------------------------- */
+/* Greedy pivoted Cholesky (src/inducing_point_selectors/conditional_variance.py:27-120) on the ALREADY PERMUTED
+ * points xp_aug (augmented layout, n rows; the numpy permutation of :60 stays on the host).
+ *   kdiag: the value diag k(x, x) takes (outputscale for RBF -- exact, as gpytorch returns it), ignored for LINEAR
+ *          where the diagonal is computed;
+ *   ci: workspace (m-1) x n doubles; di: workspace n doubles; scratch: workspace pls_cv_scratch_doubles(n) doubles;
+ *   indices_out: m int64 (positions in the permuted order; entries never reached keep the sentinel n, as :63);
+ *   n_selected_out (host int*): how many entries were filled.  Synchronises the stream before returning. */
+int64_t pls_cv_scratch_doubles(int64_t n);
+int pls_cv_select_f64(pls_ctx* ctx, int kernel_id, const double* xp_aug, int64_t n, int d, double kdiag, int m,
+                      double jitter, double threshold, int has_threshold, double* ci, double* di, double* scratch,
+                      int64_t* indices_out, int* n_selected_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PLS_B200_H_ */

@@ -1,0 +1,93 @@
+"""Builds libpls_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
+
+Called by `__graft_entry__.build()`.  Objects are compiled in parallel (one translation unit per exponent depth of
+the hot kernel) and cached by source hash under csrc/build/.
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import shutil
+import subprocess
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+BUILD = os.path.join(CSRC, "build")
+LIB = os.path.join(HERE, "libpls_b200.so")
+INCLUDE = os.path.join(os.path.dirname(HERE), "include")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17",
+    "-Xcompiler", "-fPIC",
+]
+MAX_NKD = 7
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found: libpls_b200.so cannot be built (there is no CPU fallback)")
+
+
+def _source_hash() -> str:
+    h = hashlib.sha256()
+    names = sorted(f for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h")))
+    for name in names:
+        with open(os.path.join(CSRC, name), "rb") as f:
+            h.update(name.encode())
+            h.update(f.read())
+    with open(os.path.join(INCLUDE, "pls_b200.h"), "rb") as f:
+        h.update(f.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def _units():
+    units = [("pls_api.cu", [], "pls_api.o"), ("pls_aux.cu", [], "pls_aux.o"), ("pls_selector.cu", [], "pls_selector.o"),
+             ("pls_gen_gemm.cu", [], "pls_gen_gemm.o")]
+    for k in range(1, MAX_NKD + 1):
+        units.append(("pls_gen_gemm_inst.cu", [f"-DPLS_NKD={k}"], f"pls_gen_gemm_nkd{k}.o"))
+    return units
+
+
+def build_library(force: bool = False, verbose: bool = False) -> str:
+    """Compile (if sources changed) and return the path of libpls_b200.so."""
+    stamp = os.path.join(BUILD, "source.sha256")
+    digest = _source_hash()
+    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read().strip() == digest:
+        return LIB
+    nvcc = _nvcc()
+    os.makedirs(BUILD, exist_ok=True)
+
+    def compile_one(unit):
+        src, defs, obj = unit
+        cmd = [nvcc, *NVCC_FLAGS, *defs, "-c", "-o", os.path.join(BUILD, obj), os.path.join(CSRC, src)]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {src} {defs}:\n{r.stdout}\n{r.stderr}")
+        return r.stderr
+
+    units = _units()
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 2)) as pool:
+        logs = list(pool.map(compile_one, units))
+    if verbose:
+        print("\n".join(logs))
+    objs = [os.path.join(BUILD, u[2]) for u in units]
+    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs]
+    r = subprocess.run(link, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    with open(stamp, "w") as f:
+        f.write(digest)
+    return LIB
+
+
+if __name__ == "__main__":
+    import sys
+
+    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,263 @@
+// C-ABI entry points of libpls_b200.so (declared in include/pls_b200.h): argument validation, error reporting and
+// dispatch to the kernels.  Nothing here allocates device memory or synchronises (except pls_cv_select_f64).
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "pls_aux.h"
+#include "pls_common.cuh"
+
+namespace {
+
+thread_local std::string g_create_error;
+
+int fail(pls_ctx* ctx, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (ctx) ctx->error = buf;
+  else g_create_error = buf;
+  return 1;
+}
+
+int check_cuda(pls_ctx* ctx, cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return 0;
+  return fail(ctx, "%s: %s", what, cudaGetErrorString(e));
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+int check_cost(pls_ctx* ctx, const pls_cost* c) {
+  if (!c) return fail(ctx, "cost is NULL");
+  if (c->cost_id < PLS_COST_GAUSSIAN || c->cost_id > PLS_COST_STUDENT_T) return fail(ctx, "unknown cost_id %d", c->cost_id);
+  if (c->link_id < PLS_LINK_IDENTITY || c->link_id > PLS_LINK_SQUARE) return fail(ctx, "unknown link_id %d", c->link_id);
+  return 0;
+}
+
+int check_kernel(pls_ctx* ctx, int kernel_id, int d) {
+  if (kernel_id != PLS_KERNEL_RBF && kernel_id != PLS_KERNEL_LINEAR) return fail(ctx, "unknown kernel_id %d", kernel_id);
+  if (d < 1 || d > pls::MAX_D) return fail(ctx, "input dimension d=%d outside [1, %d]", d, pls::MAX_D);
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pls_abi_version(void) { return PLS_ABI_VERSION; }
+
+int pls_ctx_create(int device, pls_ctx** out) {
+  if (!out) return fail(nullptr, "pls_ctx_create: out is NULL");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return fail(nullptr, "pls_ctx_create: no CUDA device (%s); this library has no CPU fallback", cudaGetErrorString(e));
+  if (device < 0 || device >= count) return fail(nullptr, "pls_ctx_create: device %d out of range [0, %d)", device, count);
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess)
+    return fail(nullptr, "pls_ctx_create: cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+  if (prop.major != 10)
+    return fail(nullptr, "pls_ctx_create: device %d is sm_%d%d; libpls_b200 is built for sm_100a (B200) only", device,
+                prop.major, prop.minor);
+  pls_ctx* c = new pls_ctx();
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  c->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+  *out = c;
+  return 0;
+}
+
+void pls_ctx_destroy(pls_ctx* ctx) { delete ctx; }
+
+const char* pls_last_error(const pls_ctx* ctx) { return ctx ? ctx->error.c_str() : g_create_error.c_str(); }
+
+int pls_sm_count(const pls_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
+
+int pls_point_stride(int d) {
+  if (d < 1 || d > pls::MAX_D) return -1;
+  return pls::point_stride(d);
+}
+
+int pls_backward_splits(const pls_ctx* ctx, int64_t n_rows, int64_t m, int64_t j) {
+  // Enough CTAs for >= 8 waves of one CTA per SM, a whole number of waves when possible, and splits no shorter than
+  // 16 pipeline chunks.
+  const int sms = (ctx && ctx->sm_count > 0) ? ctx->sm_count : 148;
+  const int64_t tiles = ((m + pls::BR - 1) / pls::BR) * ((j + pls::BJ - 1) / pls::BJ);
+  if (tiles <= 0 || n_rows <= 0) return 1;
+  const int64_t chunks = (n_rows + pls::BK - 1) / pls::BK;
+  int64_t max_splits = chunks / 16;
+  if (max_splits < 1) max_splits = 1;
+  int64_t want = (8LL * sms + tiles - 1) / tiles;
+  if (want < 1) want = 1;
+  if (want > max_splits) want = max_splits;
+  // look a little further for a split count that fills whole waves
+  int64_t best = want;
+  double best_eff = 0.0;
+  for (int64_t s = want; s <= want + 64 && s <= max_splits; ++s) {
+    const int64_t ctas = tiles * s;
+    const int64_t waves = (ctas + sms - 1) / sms;
+    const double eff = (double)ctas / (double)(waves * sms);
+    if (eff > best_eff + 1e-9) {
+      best_eff = eff;
+      best = s;
+    }
+  }
+  if (best > 4096) best = 4096;
+  return (int)best;
+}
+
+int pls_prepare_points_f64(pls_ctx* ctx, int kernel_id, const double* x, int64_t n, int d, int64_t ldx,
+                           const double* inv_lengthscale, const double* centre, double c_extra, double* out, void* stream) {
+  if (!ctx) return 1;
+  if (check_kernel(ctx, kernel_id, d)) return 1;
+  if (n < 0 || ldx < d || !out || (!x && n > 0)) return fail(ctx, "pls_prepare_points_f64: bad arguments");
+  pls::DimVec ls{}, ce{};
+  for (int k = 0; k < d; ++k) {
+    ls.v[k] = (kernel_id == PLS_KERNEL_RBF && inv_lengthscale) ? inv_lengthscale[k] : 1.0;
+    ce.v[k] = (kernel_id == PLS_KERNEL_RBF && centre) ? centre[k] : 0.0;
+  }
+  return check_cuda(ctx,
+                    pls::launch_prepare_points(kernel_id, x, n, d, ldx, ls, ce, c_extra, pls::point_stride(d), out,
+                                               (cudaStream_t)stream),
+                    "pls_prepare_points_f64");
+}
+
+int pls_gram_f64(pls_ctx* ctx, int kernel_id, const double* rows_aug, int64_t n_rows, const double* cols_aug,
+                 int64_t n_cols, int d, double* out, int64_t ldo, void* stream) {
+  if (!ctx) return 1;
+  if (check_kernel(ctx, kernel_id, d)) return 1;
+  if (n_rows < 0 || n_cols < 0 || ldo < n_cols || !out) return fail(ctx, "pls_gram_f64: bad arguments");
+  return check_cuda(ctx,
+                    pls::launch_gram(kernel_id, rows_aug, n_rows, cols_aug, n_cols, d, pls::point_stride(d), out, ldo,
+                                     (cudaStream_t)stream),
+                    "pls_gram_f64");
+}
+
+int pls_gemm_f64(pls_ctx* ctx, int trans_a, const double* a, int64_t lda, const double* b, int64_t ldb, double* c,
+                 int64_t ldc, int64_t rows, int64_t j, int64_t k, void* stream) {
+  if (!ctx) return 1;
+  if (rows < 0 || j < 0 || k < 0 || !a || !b || !c || ldb < j || ldc < j || lda < (trans_a ? rows : k))
+    return fail(ctx, "pls_gemm_f64: bad arguments");
+  pls::SmallGemmParams p{};
+  p.a = a; p.lda = lda; p.b = b; p.ldb = ldb; p.c = c; p.ldc = ldc; p.rows = rows; p.j = j; p.k = k;
+  return check_cuda(ctx, pls::launch_small_gemm(p, trans_a != 0, false, (cudaStream_t)stream), "pls_gemm_f64");
+}
+
+int pls_forward_f64(pls_ctx* ctx, int kernel_id, const double* xa, int64_t n, const double* za, int64_t m, int d,
+                    const double* w, int64_t ldw, int64_t j, int epilogue, const pls_cost* cost, const double* y,
+                    double* out, int64_t ldo, void* stream) {
+  if (!ctx) return 1;
+  if (check_kernel(ctx, kernel_id, d)) return 1;
+  if (epilogue < PLS_EPI_PREDICTION || epilogue > PLS_EPI_COST) return fail(ctx, "pls_forward_f64: unknown epilogue %d", epilogue);
+  if (n < 0 || m < 0 || j < 0 || !xa || !za || !w || !out) return fail(ctx, "pls_forward_f64: bad arguments");
+  if (ldw < j || (ldw & 1) || !aligned16(w)) return fail(ctx, "pls_forward_f64: w must be 16-byte aligned with an even ldw >= j");
+  if (ldo < j) return fail(ctx, "pls_forward_f64: ldo < j");
+  if (epilogue != PLS_EPI_COST && ((ldo & 1) || !aligned16(out)))
+    return fail(ctx, "pls_forward_f64: out must be 16-byte aligned with an even ldo");
+  pls::GenGemmParams p{};
+  if (epilogue != PLS_EPI_PREDICTION) {
+    if (check_cost(ctx, cost)) return 1;
+    if (!y) return fail(ctx, "pls_forward_f64: y is NULL");
+    p.cost = *cost;
+  }
+  p.rows_aug = xa; p.n_rows = n; p.red_aug = za; p.red_total = m; p.b = w; p.ldb = ldw; p.j = j;
+  p.sp = pls::point_stride(d); p.d = d; p.kernel_id = kernel_id; p.epilogue = epilogue; p.splits = 1; p.accumulate = 0;
+  p.out = out; p.ldo = ldo; p.y = y;
+  return check_cuda(ctx, pls::launch_gen_gemm_forward(ctx, p, (cudaStream_t)stream), "pls_forward_f64");
+}
+
+int pls_backward_f64(pls_ctx* ctx, int kernel_id, const double* za, int64_t m, const double* xa, int64_t n, int d,
+                     const double* dc, int64_t lddc, int64_t j, double* gp, int64_t ldg, int splits, int accumulate,
+                     void* stream) {
+  if (!ctx) return 1;
+  if (check_kernel(ctx, kernel_id, d)) return 1;
+  if (n < 0 || m < 0 || j < 0 || !xa || !za || !dc || !gp || splits < 1) return fail(ctx, "pls_backward_f64: bad arguments");
+  if (lddc < j || (lddc & 1) || !aligned16(dc)) return fail(ctx, "pls_backward_f64: dc must be 16-byte aligned with an even lddc >= j");
+  if (ldg < j || (ldg & 1) || !aligned16(gp)) return fail(ctx, "pls_backward_f64: gp must be 16-byte aligned with an even ldg >= j");
+  pls::GenGemmParams p{};
+  p.rows_aug = za; p.n_rows = m; p.red_aug = xa; p.red_total = n; p.b = dc; p.ldb = lddc; p.j = j;
+  p.sp = pls::point_stride(d); p.d = d; p.kernel_id = kernel_id; p.epilogue = -1; p.splits = splits;
+  p.accumulate = accumulate; p.out = gp; p.ldo = ldg; p.y = nullptr;
+  return check_cuda(ctx, pls::launch_gen_gemm_backward(ctx, p, (cudaStream_t)stream), "pls_backward_f64");
+}
+
+int pls_reduce_splits_f64(pls_ctx* ctx, const double* gp, int splits, int64_t rows, int64_t j, int64_t ldg, double* out,
+                          int64_t ldo, void* stream) {
+  if (!ctx) return 1;
+  if (!gp || !out || splits < 1 || rows < 0 || j < 0 || ldg < j || ldo < j) return fail(ctx, "pls_reduce_splits_f64: bad arguments");
+  return check_cuda(ctx, pls::launch_reduce_splits(gp, splits, rows, j, ldg, out, ldo, (cudaStream_t)stream), "pls_reduce_splits_f64");
+}
+
+int pls_project_update_f64(pls_ctx* ctx, const double* vt, int64_t ldv, int64_t m, int64_t m_k, const double* gm,
+                           int64_t ldg, const double* p_, int64_t ldp, int64_t j, const double* inv_lambda, double eta,
+                           int noise_mode, const double* xi, int64_t ldxi, uint64_t seed, uint64_t step,
+                           int64_t j_global_offset, int in_place, double* out, int64_t ldo, void* stream) {
+  if (!ctx) return 1;
+  if (!vt || !gm || !p_ || !inv_lambda || !out || m < 0 || m_k < 0 || j < 0 || ldv < m_k || ldg < j || ldp < j || ldo < j)
+    return fail(ctx, "pls_project_update_f64: bad arguments");
+  if (noise_mode < PLS_NOISE_NONE || noise_mode > PLS_NOISE_PHILOX) return fail(ctx, "pls_project_update_f64: unknown noise_mode %d", noise_mode);
+  if (noise_mode == PLS_NOISE_GIVEN && (!xi || ldxi < j)) return fail(ctx, "pls_project_update_f64: noise buffer missing");
+  if (in_place && (out != p_ || ldo != ldp)) return fail(ctx, "pls_project_update_f64: in_place requires out == p");
+  pls::SmallGemmParams p{};
+  p.a = vt; p.lda = ldv; p.b = gm; p.ldb = ldg; p.c = out; p.ldc = ldo; p.rows = m_k; p.j = j; p.k = m;
+  p.particles = p_; p.ldp = ldp; p.inv_lambda = inv_lambda; p.xi = xi; p.ldxi = ldxi; p.eta = eta;
+  p.noise_mode = noise_mode; p.in_place = in_place; p.seed = seed; p.step = step; p.j_global_offset = j_global_offset;
+  return check_cuda(ctx, pls::launch_small_gemm(p, true, true, (cudaStream_t)stream), "pls_project_update_f64");
+}
+
+int pls_cost_derivative_f64(pls_ctx* ctx, const pls_cost* cost, const double* y, const double* f, int64_t ldf, int64_t n,
+                            int64_t j, double* out, int64_t ldo, void* stream) {
+  if (!ctx) return 1;
+  if (check_cost(ctx, cost)) return 1;
+  if (!y || !f || !out || n < 0 || j < 0 || ldf < j || ldo < j) return fail(ctx, "pls_cost_derivative_f64: bad arguments");
+  return check_cuda(ctx, pls::launch_cost_derivative(*cost, y, f, ldf, n, j, out, ldo, ctx->sm_count, (cudaStream_t)stream),
+                    "pls_cost_derivative_f64");
+}
+
+int pls_cost_value_f64(pls_ctx* ctx, const pls_cost* cost, const double* y, const double* f, int64_t ldf, int64_t n,
+                       int64_t j, double* partial, double* out, void* stream) {
+  if (!ctx) return 1;
+  if (check_cost(ctx, cost)) return 1;
+  if (!y || !f || !out || !partial || n < 0 || j < 0 || ldf < j) return fail(ctx, "pls_cost_value_f64: bad arguments");
+  if (check_cuda(ctx, pls::launch_cost_value(*cost, y, f, ldf, n, j, partial, (cudaStream_t)stream), "pls_cost_value_f64")) return 1;
+  return check_cuda(ctx, pls::launch_energy_terms(partial, (n + 127) / 128, j, nullptr, 0, 0, nullptr, j, out, (cudaStream_t)stream),
+                    "pls_cost_value_f64");
+}
+
+int pls_energy_terms_f64(pls_ctx* ctx, const double* partial, int64_t tiles, int64_t ldpart, const double* p, int64_t ldp,
+                         int64_t m_k, const double* inv_lambda, int64_t j, double* out, void* stream) {
+  if (!ctx) return 1;
+  if (!partial || !out || tiles < 0 || ldpart < j || j < 0) return fail(ctx, "pls_energy_terms_f64: bad arguments");
+  if (p && (!inv_lambda || ldp < j || m_k < 0)) return fail(ctx, "pls_energy_terms_f64: bad particle arguments");
+  return check_cuda(ctx, pls::launch_energy_terms(partial, tiles, ldpart, p, ldp, m_k, inv_lambda, j, out, (cudaStream_t)stream),
+                    "pls_energy_terms_f64");
+}
+
+int pls_philox_normal_f64(pls_ctx* ctx, uint64_t seed, uint64_t step, int64_t rows, int64_t j, int64_t j_global_offset,
+                          double* out, int64_t ldo, void* stream) {
+  if (!ctx) return 1;
+  if (!out || rows < 0 || j < 0 || ldo < j) return fail(ctx, "pls_philox_normal_f64: bad arguments");
+  return check_cuda(ctx, pls::launch_philox_fill(seed, step, rows, j, j_global_offset, out, ldo, (cudaStream_t)stream),
+                    "pls_philox_normal_f64");
+}
+
+int64_t pls_cv_scratch_doubles(int64_t n) { return n < 0 ? 0 : pls::cv_scratch_doubles(n); }
+
+int pls_cv_select_f64(pls_ctx* ctx, int kernel_id, const double* xp_aug, int64_t n, int d, double kdiag, int m,
+                      double jitter, double threshold, int has_threshold, double* ci, double* di, double* scratch,
+                      int64_t* indices_out, int* n_selected_out, void* stream) {
+  if (!ctx) return 1;
+  if (check_kernel(ctx, kernel_id, d)) return 1;
+  if (!xp_aug || !ci || !di || !scratch || !indices_out || !n_selected_out) return fail(ctx, "pls_cv_select_f64: NULL argument");
+  if (m < 2) return fail(ctx, "pls_cv_select_f64: Must have at least 2 inducing points");
+  if (n < m) return fail(ctx, "pls_cv_select_f64: m=%d exceeds the number of points n=%lld", m, (long long)n);
+  return check_cuda(ctx,
+                    pls::run_cv_select(ctx, kernel_id, xp_aug, n, d, kdiag, m, jitter, threshold, has_threshold, ci, di,
+                                       scratch, indices_out, n_selected_out, (cudaStream_t)stream),
+                    "pls_cv_select_f64");
+}
+
+}  // extern "C"

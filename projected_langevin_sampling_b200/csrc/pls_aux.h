@@ -1,0 +1,56 @@
+// Internal declarations of the auxiliary kernels (pls_aux.cu) and the selector (pls_selector.cu).
+#pragma once
+#include "pls_internal.h"
+
+namespace pls {
+
+constexpr int MAX_D = 26;  // D + 2 <= 28 = 4 * MAX_NKD
+
+struct DimVec {
+  double v[MAX_D];
+};
+
+struct SmallGemmParams {
+  const double* a;
+  int64_t lda;
+  const double* b;
+  int64_t ldb;
+  double* c;
+  int64_t ldc;
+  int64_t rows, j, k;
+  // Langevin-update epilogue (orthonormal.py:151-158)
+  const double* particles;
+  int64_t ldp;
+  const double* inv_lambda;
+  const double* xi;
+  int64_t ldxi;
+  double eta;
+  int noise_mode;
+  int in_place;
+  uint64_t seed, step;
+  int64_t j_global_offset;
+};
+
+cudaError_t launch_prepare_points(int kernel_id, const double* x, int64_t n, int d, int64_t ldx, const DimVec& inv_ls,
+                                  const DimVec& centre, double c_extra, int sp, double* out, cudaStream_t stream);
+cudaError_t launch_gram(int kernel_id, const double* ra, int64_t nr, const double* ca, int64_t nc, int d, int sp,
+                        double* out, int64_t ldo, cudaStream_t stream);
+cudaError_t launch_philox_fill(uint64_t seed, uint64_t step, int64_t rows, int64_t j, int64_t joff, double* out,
+                               int64_t ldo, cudaStream_t stream);
+cudaError_t launch_small_gemm(const SmallGemmParams& p, bool trans_a, bool update, cudaStream_t stream);
+cudaError_t launch_reduce_splits(const double* gp, int splits, int64_t rows, int64_t j, int64_t ldg, double* out,
+                                 int64_t ldo, cudaStream_t stream);
+cudaError_t launch_cost_derivative(const pls_cost& cost, const double* y, const double* f, int64_t ldf, int64_t n,
+                                   int64_t j, double* out, int64_t ldo, int sm_count, cudaStream_t stream);
+cudaError_t launch_cost_value(const pls_cost& cost, const double* y, const double* f, int64_t ldf, int64_t n, int64_t j,
+                              double* partial, cudaStream_t stream);
+cudaError_t launch_energy_terms(const double* partial, int64_t tiles, int64_t ldpart, const double* p, int64_t ldp,
+                                int64_t m_k, const double* inv_lambda, int64_t j, double* out, cudaStream_t stream);
+
+// ConditionalVariance selector (pls_selector.cu)
+int64_t cv_scratch_doubles(int64_t n);
+cudaError_t run_cv_select(const pls_ctx* ctx, int kernel_id, const double* xp_aug, int64_t n, int d, double kdiag, int m,
+                          double jitter, double threshold, int has_threshold, double* ci, double* di, double* scratch,
+                          int64_t* indices_out, int* n_selected_out, cudaStream_t stream);
+
+}  // namespace pls

@@ -1,0 +1,121 @@
+// Per-point likelihood cost and its derivative w.r.t. the untransformed prediction F, evaluated in registers.
+// Follows the reference's formulas operation by operation (paths relative to the reference root,
+// pls/ = src/projected_langevin_sampling/):
+//   links     pls/link_functions.py:30-80
+//   gaussian  pls/costs/gaussian.py:54-88       bernoulli  pls/costs/bernoulli.py:48-77
+//   poisson   pls/costs/poisson.py:47-82        student-t  pls/costs/student_t.py:55-88
+//   multimodal pls/costs/multimodal.py:37-77 (derivative: closed form of the autograd the reference runs, :79-91)
+// For (cost, link) pairs without a hand-written derivative in the reference, the derivative is the chain rule
+// (d cost / d mu) * link'(F), which is what its autograd fallback pls/costs/base.py:68-84 evaluates; torch's clip has
+// zero gradient outside [jitter, 1 - jitter], reproduced in link_derivative.
+#pragma once
+#include "pls_common.cuh"
+
+namespace pls {
+
+__device__ __forceinline__ double clip(double v, double lo, double hi) { return fmin(fmax(v, lo), hi); }
+
+__device__ __forceinline__ double link_transform(const pls_cost& c, double f) {
+  switch (c.link_id) {
+    case PLS_LINK_SQUARE:
+      return f * f;
+    case PLS_LINK_SIGMOID:
+      return clip(1.0 / (1.0 + exp(-f)), c.link_jitter, 1.0 - c.link_jitter);
+    case PLS_LINK_PROBIT:
+      return clip((1.0 + erf(f / c.probit_divisor)) / 2.0, c.link_jitter, 1.0 - c.link_jitter);
+    default:
+      return f;
+  }
+}
+
+__device__ __forceinline__ double link_derivative(const pls_cost& c, double f) {
+  switch (c.link_id) {
+    case PLS_LINK_SQUARE:
+      return 2.0 * f;
+    case PLS_LINK_SIGMOID: {
+      const double s = 1.0 / (1.0 + exp(-f));
+      return (s >= c.link_jitter && s <= 1.0 - c.link_jitter) ? s * (1.0 - s) : 0.0;
+    }
+    case PLS_LINK_PROBIT: {
+      const double u = f / c.probit_divisor;
+      const double p = (1.0 + erf(u)) / 2.0;
+      // d/df [ (1 + erf(f / r)) / 2 ] = exp(-(f/r)^2) / (r sqrt(pi))
+      return (p >= c.link_jitter && p <= 1.0 - c.link_jitter) ? exp(-u * u) / (c.probit_divisor * 1.7724538509055160273) : 0.0;
+    }
+    default:
+      return 1.0;
+  }
+}
+
+// c(y, F) for one training point
+__device__ __forceinline__ double cost_value(const pls_cost& c, double y, double f) {
+  const double mu = link_transform(c, f);
+  switch (c.cost_id) {
+    case PLS_COST_GAUSSIAN: {
+      const double e = mu - y;
+      return (1.0 / (2.0 * c.observation_noise)) * (e * e);
+    }
+    case PLS_COST_BERNOULLI:
+      return -log(mu) * y - log(1.0 - mu) * (1.0 - y);
+    case PLS_COST_POISSON:
+      return -2.0 * (y * log(fabs(f))) + mu;
+    case PLS_COST_STUDENT_T: {
+      const double e = mu - y;
+      return 0.5 * (c.degrees_of_freedom + 1.0) * log(1.0 + (e * e) / (c.degrees_of_freedom * (c.scale * c.scale)));
+    }
+    case PLS_COST_MULTIMODAL: {
+      const double s2 = c.observation_noise * c.observation_noise;
+      const double e1 = y - mu + c.shift;
+      const double e2 = y - mu;
+      const double lognorm = log(sqrt(2.0 * 3.141592653589793238 * s2));
+      const double a1 = log(c.bernoulli_noise) + (-0.5 * (e1 * e1 / s2) - lognorm);
+      const double a2 = log(1.0 - c.bernoulli_noise) + (-0.5 * (e2 * e2 / s2) - lognorm);
+      const double mx = fmax(a1, a2);
+      return -(mx + log(exp(a1 - mx) + exp(a2 - mx)));
+    }
+  }
+  return 0.0;
+}
+
+// d c(y, F) / d F for one training point
+__device__ __forceinline__ double cost_derivative(const pls_cost& c, double y, double f) {
+  if (c.closed_form) {
+    if (c.cost_id == PLS_COST_GAUSSIAN && c.link_id == PLS_LINK_IDENTITY) return (1.0 / c.observation_noise) * (f - y);
+    if (c.cost_id == PLS_COST_BERNOULLI && c.link_id == PLS_LINK_SIGMOID) {
+      const double p = link_transform(c, f);  // the clipped probability, as bernoulli.py:72-77 uses it
+      return -(y * (1.0 - p)) + (1.0 - y) * p;
+    }
+    if (c.cost_id == PLS_COST_POISSON && c.link_id == PLS_LINK_SQUARE) return -2.0 * (y / f) + 2.0 * f;
+    if (c.cost_id == PLS_COST_STUDENT_T && c.link_id == PLS_LINK_IDENTITY) {
+      const double e = f - y;
+      return (c.degrees_of_freedom + 1.0) * (e / (c.degrees_of_freedom * (c.scale * c.scale) + e * e));
+    }
+  }
+  const double mu = link_transform(c, f);
+  const double dmu = link_derivative(c, f);
+  switch (c.cost_id) {
+    case PLS_COST_GAUSSIAN:
+      return (mu - y) / c.observation_noise * dmu;
+    case PLS_COST_BERNOULLI:
+      return (-y / mu + (1.0 - y) / (1.0 - mu)) * dmu;
+    case PLS_COST_POISSON:
+      return -2.0 * y / f + dmu;
+    case PLS_COST_STUDENT_T: {
+      const double e = mu - y;
+      return (c.degrees_of_freedom + 1.0) * e / (c.degrees_of_freedom * c.scale * c.scale + e * e) * dmu;
+    }
+    case PLS_COST_MULTIMODAL: {
+      const double s2 = c.observation_noise * c.observation_noise;
+      const double e1 = y - mu + c.shift;
+      const double e2 = y - mu;
+      const double a1 = log(c.bernoulli_noise) - 0.5 * e1 * e1 / s2;
+      const double a2 = log(1.0 - c.bernoulli_noise) - 0.5 * e2 * e2 / s2;
+      const double mx = fmax(a1, a2);
+      const double w1 = exp(a1 - mx), w2 = exp(a2 - mx);
+      return -((w1 * e1 + w2 * e2) / (w1 + w2)) / s2 * dmu;
+    }
+  }
+  return 0.0;
+}
+
+}  // namespace pls

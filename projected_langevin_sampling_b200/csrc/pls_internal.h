@@ -1,0 +1,43 @@
+// Internal (non-ABI) declarations shared by the csrc translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/pls_b200.h"
+
+struct pls_ctx {
+  int device = 0;
+  int sm_count = 0;
+  int max_smem_optin = 0;
+  std::string error;
+};
+
+namespace pls {
+
+// Parameters of the generated-operand GEMM  C[r][j] (+)= sum_k kappa(row_r, red_k) * B[k][j]
+struct GenGemmParams {
+  const double* rows_aug;  // row-side augmented points (n_rows x sp)
+  int64_t n_rows;
+  const double* red_aug;  // reduction-side augmented points (red_total x sp)
+  int64_t red_total;
+  const double* b;  // streamed matrix (red_total x ldb)
+  int64_t ldb;
+  int64_t j;  // valid columns
+  int sp;
+  int d;
+  int kernel_id;
+  int epilogue;  // PLS_EPI_* for the forward role; ignored by the backward role
+  int splits;    // backward role: number of reduction splits (gridDim = tiles * splits)
+  int accumulate;
+  double* out;
+  int64_t ldo;
+  const double* y;
+  pls_cost cost;
+};
+
+cudaError_t launch_gen_gemm_forward(const pls_ctx* ctx, const GenGemmParams& p, cudaStream_t stream);
+cudaError_t launch_gen_gemm_backward(const pls_ctx* ctx, const GenGemmParams& p, cudaStream_t stream);
+
+}  // namespace pls

@@ -1,0 +1,113 @@
+"""Launch sequence and workspaces of the fused Langevin step on one GPU.
+
+One step (reference: PLS.calculate_particle_update, src/projected_langevin_sampling/projected_langevin_sampling.py:107-123
+-> orthonormal.py:98-108, costs/*.py, orthonormal.py:128-159) becomes
+
+    W  = V~ P                                  pls_gemm_f64            (M x J; 2 M M_k J flops)
+    for each chunk of training rows:
+        Dc = d_2 c(y, k(X_c, Z) W)             pls_forward_f64         (Gram tiles generated on the fly, cost in registers)
+        Gp += k(Z, X_c) Dc                     pls_backward_f64        (Gram tiles generated on the fly, split over rows)
+    G' = sum_s Gp[s]                           pls_reduce_splits_f64   (deterministic order)
+    [all-reduce G' over the N-shard group]     torch.distributed / NCCL, only when the training rows are sharded
+    P += -eta V~^T G' - eta P / lambda + sqrt(2 eta) xi      pls_project_update_f64
+
+The N x M Gram and the N x J prediction matrix are never materialised; the only N-sized intermediate is the Dc chunk
+(`dc_budget_bytes`, default 8 GiB), written and read once per step (~2 % of the step time at the headline shape).
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Tuple
+
+import torch
+
+from . import _native as nat
+from . import ops
+
+DEFAULT_DC_BUDGET = 8 << 30
+ROW_ALIGN = 128
+
+
+class LangevinEngine:
+    def __init__(self, ctx: nat.Context, kernel_id: int, d: int, xa: torch.Tensor, za: torch.Tensor, vt: torch.Tensor,
+                 inv_lambda: torch.Tensor, j: int, dc_budget_bytes: int = DEFAULT_DC_BUDGET,
+                 gradient_reduce: Optional[Callable[[torch.Tensor], None]] = None):
+        self.ctx, self.kernel_id, self.d = ctx, kernel_id, d
+        self.xa, self.za, self.vt, self.inv_lambda = xa, za, vt, inv_lambda
+        self.n, self.m, self.m_k, self.j = xa.shape[0], za.shape[0], vt.shape[1], j
+        self.gradient_reduce = gradient_reduce
+        dev = xa.device
+        self.ldj = ops.even(j)
+        rows = max(ROW_ALIGN, (dc_budget_bytes // (self.ldj * 8)) // ROW_ALIGN * ROW_ALIGN)
+        self.chunk_rows = min(self.n, rows)
+        self.chunks: List[Tuple[int, int]] = [(r, min(r + self.chunk_rows, self.n)) for r in range(0, self.n, self.chunk_rows)]
+        self.w = torch.zeros((self.m, self.ldj), dtype=torch.float64, device=dev)
+        self.gm = torch.zeros((self.m, self.ldj), dtype=torch.float64, device=dev)
+        self.dc = torch.zeros((self.chunk_rows, self.ldj), dtype=torch.float64, device=dev)
+        self.splits = ops.backward_splits(ctx, self.chunk_rows, self.m, j)
+        self.gp = torch.zeros((self.splits, self.m, self.ldj), dtype=torch.float64, device=dev)
+
+    # ---- pieces ------------------------------------------------------------------------------------------------------
+    def _weights(self, particles: torch.Tensor) -> torch.Tensor:
+        return ops.gemm(self.ctx, self.vt, particles, self.w)  # W = V~ P
+
+    def gradient(self, particles: torch.Tensor, cost: nat.PlsCost, y: torch.Tensor) -> torch.Tensor:
+        """G' = k(Z, X) d_2 c(y, k(X, Z) V~ P)  -> (M, ldj) workspace view."""
+        self._weights(particles)
+        for ci, (r0, r1) in enumerate(self.chunks):
+            dc = self.dc[: r1 - r0]
+            ops.forward(self.ctx, self.kernel_id, self.xa[r0:r1], self.za, self.d, self.w, self.j, nat.EPI_COST_DERIVATIVE,
+                        dc, cost=cost, y=y[r0:r1])
+            ops.backward(self.ctx, self.kernel_id, self.za, self.xa[r0:r1], self.d, dc, self.j, self.gp, self.splits,
+                         accumulate=ci > 0)
+        ops.reduce_splits(self.ctx, self.gp, self.j, self.gm)
+        if self.gradient_reduce is not None:
+            self.gradient_reduce(self.gm)
+        return self.gm
+
+    def step(self, particles: torch.Tensor, eta: float, cost: nat.PlsCost, y: torch.Tensor, out: torch.Tensor,
+             noise_mode: int, xi: Optional[torch.Tensor] = None, seed: int = 0, step_index: int = 0,
+             j_global_offset: int = 0, in_place: bool = False) -> torch.Tensor:
+        gm = self.gradient(particles, cost, y)
+        return ops.project_update(self.ctx, self.vt, gm, particles, self.j, self.inv_lambda, eta, out, noise_mode=noise_mode,
+                                  xi=xi, seed=seed, step=step_index, j_global_offset=j_global_offset, in_place=in_place)
+
+    def prediction(self, particles: torch.Tensor) -> torch.Tensor:
+        """F = k(X, Z) V~ P  -> (N, J)  (materialised: API parity / small problems only)."""
+        self._weights(particles)
+        out, _ = ops.alloc_matrix(self.n, self.j, self.xa.device)
+        ops.forward(self.ctx, self.kernel_id, self.xa, self.za, self.d, self.w, self.j, nat.EPI_PREDICTION, out)
+        return out[:, : self.j]
+
+    def cost_derivative(self, particles: torch.Tensor, cost: nat.PlsCost, y: torch.Tensor) -> torch.Tensor:
+        self._weights(particles)
+        out, _ = ops.alloc_matrix(self.n, self.j, self.xa.device)
+        ops.forward(self.ctx, self.kernel_id, self.xa, self.za, self.d, self.w, self.j, nat.EPI_COST_DERIVATIVE, out, cost=cost, y=y)
+        return out[:, : self.j]
+
+    def cost_partials(self, particles: torch.Tensor, cost: nat.PlsCost, y: torch.Tensor) -> torch.Tensor:
+        """per-128-row-tile column sums of c(y, F) -> (tiles, J) without materialising F."""
+        self._weights(particles)
+        tiles = (self.n + nat.TILE_ROWS - 1) // nat.TILE_ROWS
+        part = torch.empty((max(tiles, 1), self.ldj), dtype=torch.float64, device=self.xa.device)
+        ops.forward(self.ctx, self.kernel_id, self.xa, self.za, self.d, self.w, self.j, nat.EPI_COST, part, cost=cost, y=y)
+        return part
+
+    def cost(self, particles: torch.Tensor, cost: nat.PlsCost, y: torch.Tensor) -> torch.Tensor:
+        return ops.energy_terms(self.ctx, self.cost_partials(particles, cost, y), self.j, None, None)
+
+    def backproject_update(self, particles: torch.Tensor, cost_derivative: torch.Tensor, eta: float, out: torch.Tensor,
+                           noise_mode: int, xi: Optional[torch.Tensor]) -> torch.Tensor:
+        """Update from a caller-provided Dc (N x J): OrthonormalBasis._calculate_particle_update."""
+        dc = cost_derivative
+        if dc.stride(1) != 1 or (dc.stride(0) & 1) or (dc.data_ptr() & 15):
+            buf, _ = ops.alloc_matrix(self.n, self.j, dc.device)
+            buf[:, : self.j].copy_(dc)
+            dc = buf[:, : self.j]
+        splits = ops.backward_splits(self.ctx, self.n, self.m, self.j)
+        gp = torch.empty((splits, self.m, self.ldj), dtype=torch.float64, device=dc.device)
+        ops.backward(self.ctx, self.kernel_id, self.za, self.xa, self.d, dc, self.j, gp, splits, accumulate=False)
+        ops.reduce_splits(self.ctx, gp, self.j, self.gm)
+        if self.gradient_reduce is not None:
+            self.gradient_reduce(self.gm)
+        return ops.project_update(self.ctx, self.vt, self.gm, particles, self.j, self.inv_lambda, eta, out,
+                                  noise_mode=noise_mode, xi=xi)

@@ -1,0 +1,180 @@
+"""Tensor-level wrappers over the C ABI (one Python function per entry point of include/pls_b200.h).
+
+Every function takes float64 CUDA tensors, passes raw pointers + leading dimensions, enqueues on torch's current
+stream and returns tensors that it allocated with torch (device memory management is torch's job, the arithmetic
+is the library's).  `ctx.launches` counts the kernels enqueued (bench.py reports it as `gpu_launches`).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _native as nat
+
+F64 = torch.float64
+
+
+def even(n: int) -> int:
+    """Leading dimensions of streamed matrices must be even (16-byte rows for the bulk copies)."""
+    return n + (n & 1)
+
+
+def as_device_f64(t: torch.Tensor, device: Optional[torch.device] = None) -> torch.Tensor:
+    dev = device or torch.device("cuda", torch.cuda.current_device())
+    return t.detach().to(device=dev, dtype=F64).contiguous()
+
+
+def alloc_matrix(rows: int, cols: int, device) -> Tuple[torch.Tensor, int]:
+    """rows x even(cols) storage; returns (storage, ld).  Use storage[:, :cols] as the logical matrix."""
+    ld = even(cols)
+    return torch.empty((rows, ld), dtype=F64, device=device), ld
+
+
+def _ld(t: torch.Tensor) -> int:
+    assert t.dim() == 2 and t.stride(1) == 1, "matrix must be row-major with unit column stride"
+    return t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1])
+
+
+def _dbl_array(values: Sequence[float]):
+    arr = (C.c_double * len(values))(*[float(v) for v in values])
+    return arr
+
+
+# ---- setup ------------------------------------------------------------------------------------------------------
+def prepare_points(ctx: nat.Context, kernel_id: int, x: torch.Tensor, inv_lengthscale: Sequence[float],
+                   centre: Sequence[float], c_extra: float) -> torch.Tensor:
+    """x (n x D) -> augmented layout (n x SP), see include/pls_b200.h."""
+    nat.require_cuda_tensor(x, "x")
+    n, d = x.shape
+    sp = nat.point_stride(d)
+    out = torch.empty((n, sp), dtype=F64, device=x.device)
+    ctx.check(ctx.lib.pls_prepare_points_f64(ctx.handle, kernel_id, x.data_ptr(), n, d, _ld(x), _dbl_array(inv_lengthscale),
+                                             _dbl_array(centre), float(c_extra), out.data_ptr(), ctx.stream()))
+    ctx.launches += 1
+    return out
+
+
+def gram(ctx: nat.Context, kernel_id: int, rows_aug: torch.Tensor, cols_aug: torch.Tensor, d: int) -> torch.Tensor:
+    out = torch.empty((rows_aug.shape[0], cols_aug.shape[0]), dtype=F64, device=rows_aug.device)
+    if out.numel():
+        ctx.check(ctx.lib.pls_gram_f64(ctx.handle, kernel_id, rows_aug.data_ptr(), rows_aug.shape[0], cols_aug.data_ptr(),
+                                       cols_aug.shape[0], d, out.data_ptr(), max(out.shape[1], 1), ctx.stream()))
+        ctx.launches += 1
+    return out
+
+
+# ---- step pieces ---------------------------------------------------------------------------------------------------
+def gemm(ctx: nat.Context, a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, trans_a: bool = False) -> torch.Tensor:
+    """out[:, :j] = op(a) @ b[:, :j];  a, b, out row-major 2-D (views with a row stride are fine)."""
+    rows = a.shape[1] if trans_a else a.shape[0]
+    k = a.shape[0] if trans_a else a.shape[1]
+    j = b.shape[1]
+    assert b.shape[0] == k and out.shape[0] == rows and out.shape[1] >= j
+    ctx.check(ctx.lib.pls_gemm_f64(ctx.handle, int(trans_a), a.data_ptr(), _ld(a), b.data_ptr(), _ld(b), out.data_ptr(),
+                                   _ld(out), rows, j, k, ctx.stream()))
+    ctx.launches += 1
+    return out
+
+
+def forward(ctx: nat.Context, kernel_id: int, xa: torch.Tensor, za: torch.Tensor, d: int, w: torch.Tensor, j: int,
+            epilogue: int, out: torch.Tensor, cost: Optional[nat.PlsCost] = None, y: Optional[torch.Tensor] = None) -> torch.Tensor:
+    ctx.check(ctx.lib.pls_forward_f64(ctx.handle, kernel_id, xa.data_ptr(), xa.shape[0], za.data_ptr(), za.shape[0], d,
+                                      w.data_ptr(), _ld(w), j, epilogue, C.byref(cost) if cost is not None else None,
+                                      nat.ptr(y), out.data_ptr(), _ld(out), ctx.stream()))
+    ctx.launches += 1
+    return out
+
+
+def backward(ctx: nat.Context, kernel_id: int, za: torch.Tensor, xa: torch.Tensor, d: int, dc: torch.Tensor, j: int,
+             gp: torch.Tensor, splits: int, accumulate: bool) -> torch.Tensor:
+    """gp: (splits, M, ld) storage."""
+    assert gp.dim() == 3 and gp.shape[0] == splits and gp.shape[1] == za.shape[0] and gp.is_contiguous()
+    ctx.check(ctx.lib.pls_backward_f64(ctx.handle, kernel_id, za.data_ptr(), za.shape[0], xa.data_ptr(), xa.shape[0], d,
+                                       dc.data_ptr(), _ld(dc), j, gp.data_ptr(), gp.shape[2], splits, int(accumulate),
+                                       ctx.stream()))
+    ctx.launches += 1
+    return gp
+
+
+def backward_splits(ctx: nat.Context, n_rows: int, m: int, j: int) -> int:
+    return int(ctx.lib.pls_backward_splits(ctx.handle, n_rows, m, j))
+
+
+def reduce_splits(ctx: nat.Context, gp: torch.Tensor, j: int, out: torch.Tensor) -> torch.Tensor:
+    ctx.check(ctx.lib.pls_reduce_splits_f64(ctx.handle, gp.data_ptr(), gp.shape[0], gp.shape[1], j, gp.shape[2],
+                                            out.data_ptr(), _ld(out), ctx.stream()))
+    ctx.launches += 1
+    return out
+
+
+def project_update(ctx: nat.Context, vt: torch.Tensor, gm: torch.Tensor, p: torch.Tensor, j: int, inv_lambda: torch.Tensor,
+                   eta: float, out: torch.Tensor, noise_mode: int = nat.NOISE_NONE, xi: Optional[torch.Tensor] = None,
+                   seed: int = 0, step: int = 0, j_global_offset: int = 0, in_place: bool = False) -> torch.Tensor:
+    m, m_k = vt.shape
+    ctx.check(ctx.lib.pls_project_update_f64(ctx.handle, vt.data_ptr(), _ld(vt), m, m_k, gm.data_ptr(), _ld(gm), p.data_ptr(),
+                                             _ld(p), j, inv_lambda.data_ptr(), float(eta), noise_mode, nat.ptr(xi),
+                                             _ld(xi) if xi is not None else 0, seed & (2**64 - 1), step & (2**64 - 1),
+                                             j_global_offset, int(in_place), out.data_ptr(), _ld(out), ctx.stream()))
+    ctx.launches += 1
+    return out
+
+
+def cost_derivative(ctx: nat.Context, cost: nat.PlsCost, y: torch.Tensor, f: torch.Tensor) -> torch.Tensor:
+    n, j = f.shape
+    out = torch.empty((n, j), dtype=F64, device=f.device)
+    if out.numel():
+        ctx.check(ctx.lib.pls_cost_derivative_f64(ctx.handle, C.byref(cost), y.data_ptr(), f.data_ptr(), _ld(f), n, j,
+                                                  out.data_ptr(), max(j, 1), ctx.stream()))
+        ctx.launches += 1
+    return out
+
+
+def cost_value(ctx: nat.Context, cost: nat.PlsCost, y: torch.Tensor, f: torch.Tensor) -> torch.Tensor:
+    n, j = f.shape
+    tiles = (n + nat.TILE_ROWS - 1) // nat.TILE_ROWS
+    partial = torch.empty((max(tiles, 1), j), dtype=F64, device=f.device)
+    out = torch.empty((j,), dtype=F64, device=f.device)
+    ctx.check(ctx.lib.pls_cost_value_f64(ctx.handle, C.byref(cost), y.data_ptr(), f.data_ptr(), _ld(f), n, j,
+                                         partial.data_ptr(), out.data_ptr(), ctx.stream()))
+    ctx.launches += 2
+    return out
+
+
+def energy_terms(ctx: nat.Context, partial: torch.Tensor, j: int, p: Optional[torch.Tensor],
+                 inv_lambda: Optional[torch.Tensor]) -> torch.Tensor:
+    out = torch.empty((j,), dtype=F64, device=partial.device)
+    ctx.check(ctx.lib.pls_energy_terms_f64(ctx.handle, partial.data_ptr(), partial.shape[0], _ld(partial), nat.ptr(p),
+                                           _ld(p) if p is not None else 0, p.shape[0] if p is not None else 0,
+                                           nat.ptr(inv_lambda), j, out.data_ptr(), ctx.stream()))
+    ctx.launches += 1
+    return out
+
+
+def philox_normal(ctx: nat.Context, seed: int, step: int, rows: int, j: int, j_global_offset: int = 0,
+                  device=None) -> torch.Tensor:
+    out = torch.empty((rows, j), dtype=F64, device=device or torch.device("cuda", ctx.device_index))
+    ctx.check(ctx.lib.pls_philox_normal_f64(ctx.handle, seed & (2**64 - 1), step & (2**64 - 1), rows, j, j_global_offset,
+                                            out.data_ptr(), max(j, 1), ctx.stream()))
+    ctx.launches += 1
+    return out
+
+
+def cv_select(ctx: nat.Context, kernel_id: int, xp_aug: torch.Tensor, d: int, kdiag: float, m: int, jitter: float,
+              threshold: Optional[float]) -> Tuple[torch.Tensor, int]:
+    """Returns (indices into the permuted order (m,), number selected)."""
+    n = xp_aug.shape[0]
+    dev = xp_aug.device
+    ci = torch.empty((m - 1, n), dtype=F64, device=dev)
+    di = torch.empty((n,), dtype=F64, device=dev)
+    scratch = torch.zeros((int(ctx.lib.pls_cv_scratch_doubles(n)),), dtype=F64, device=dev)
+    indices = torch.full((m,), n, dtype=torch.int64, device=dev)  # sentinel N, as conditional_variance.py:63
+    nsel = C.c_int(0)
+    ctx.check(ctx.lib.pls_cv_select_f64(ctx.handle, kernel_id, xp_aug.data_ptr(), n, d, float(kdiag), m, float(jitter),
+                                        float(threshold) if threshold is not None else 0.0, int(threshold is not None),
+                                        ci.data_ptr(), di.data_ptr(), scratch.data_ptr(), indices.data_ptr(),
+                                        C.byref(nsel), ctx.stream()))
+    ctx.launches += 2 * m
+    return indices, int(nsel.value)

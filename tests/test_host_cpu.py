@@ -1,0 +1,182 @@
+"""CPU-side checks (no GPU): the C-ABI library loads and exports every symbol include/pls_b200.h declares, layout
+helpers, host-side argument logic, the product never touches the oracle, and the multi-process partition logic under
+gloo with world_size 2."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_functions():
+    text = open(os.path.join(ROOT, "include", "pls_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(pls_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from projected_langevin_sampling_b200 import _native
+
+    names = _declared_functions()
+    assert len(names) >= 18
+    assert sorted(_native.SIGNATURES) == names  # the binding covers exactly the header
+    lib = ctypes.CDLL(_native.LIB_PATH)
+    for n in names:
+        assert hasattr(lib, n), n
+    assert _native.load_library().pls_abi_version() == _native.ABI_VERSION
+
+
+def test_layout_helpers():
+    from projected_langevin_sampling_b200 import _native
+
+    lib = _native.load_library()
+    # smallest stride >= D + 2 that is 4 mod 8 (bank-conflict-free point tiles, 16-byte rows)
+    assert [lib.pls_point_stride(d) for d in (1, 2, 3, 8, 10, 11, 16, 18, 19, 26)] == [4, 4, 12, 12, 12, 20, 20, 20, 28, 28]
+    assert lib.pls_point_stride(0) == -1 and lib.pls_point_stride(27) == -1
+    with pytest.raises(ValueError):
+        _native.point_stride(40)
+    # headline shape: 8 x 32 = 256 output tiles -> 37 splits = 9472 CTAs = 64 whole waves of 148
+    s = lib.pls_backward_splits(None, 1_000_000, 1024, 4096)
+    assert (256 * s) % 148 == 0 and s >= 4
+    assert lib.pls_backward_splits(None, 100, 10, 100) == 1  # tiny problems are not split
+    assert lib.pls_cv_scratch_doubles(1000) >= 8 + 3 * 4 + 125
+
+
+def test_no_gpu_fails_loudly():
+    from projected_langevin_sampling_b200 import _native
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(_native.NativeLibraryError):
+        _native.context()
+    lib = _native.load_library()
+    h = ctypes.c_void_p()
+    assert lib.pls_ctx_create(0, ctypes.byref(h)) != 0
+    assert b"no CUDA device" in lib.pls_last_error(None)
+    import projected_langevin_sampling_b200 as pkg
+
+    with pytest.raises(_native.NativeLibraryError):  # no silent CPU fallback anywhere on the path
+        pkg.OrthonormalBasis(pkg.PLSKernel(pkg.LinearKernel(), torch.ones(2, 2)), torch.ones(2, 2), torch.ones(3, 2))
+
+
+def test_kernel_spec_duck_typing():
+    from projected_langevin_sampling_b200 import _native, kernels
+
+    k = kernels.ScaleKernel(kernels.RBFKernel(ard_num_dims=3, lengthscale=torch.tensor([[1.0, 2.0, 4.0]])), outputscale=2.5)
+    spec = kernels.kernel_spec(k, 3)
+    assert spec.kernel_id == _native.KERNEL_RBF and spec.lengthscale == [1.0, 2.0, 4.0] and spec.outputscale == 2.5
+    assert spec.inv_lengthscale == [1.0, 0.5, 0.25]
+    assert kernels.kernel_spec(kernels.ScaleKernel(kernels.RBFKernel(lengthscale=0.15), 3.0), 2).lengthscale == [0.15, 0.15]
+
+    class RBFKernel:  # a gpytorch-like object: only the attribute names matter
+        lengthscale = torch.tensor([[0.7]])
+
+    class ScaleKernel:
+        base_kernel = RBFKernel()
+        outputscale = torch.tensor(1.9)
+
+    spec = kernels.kernel_spec(ScaleKernel(), 1)
+    assert spec.kernel_id == _native.KERNEL_RBF and abs(spec.outputscale - 1.9) < 1e-7
+
+    class MockKernel:
+        pass
+
+    assert kernels.kernel_spec(MockKernel(), 2).kernel_id == _native.KERNEL_LINEAR
+
+    class Matern:
+        pass
+
+    with pytest.raises(TypeError):
+        kernels.kernel_spec(Matern(), 2)
+    with pytest.raises(ValueError):
+        kernels.kernel_spec(k, 5)
+
+
+def test_cost_native_struct():
+    from projected_langevin_sampling_b200 import _native as nat
+    from projected_langevin_sampling_b200.projected_langevin_sampling import costs, link_functions as lf
+
+    y = torch.zeros(3)
+    c = costs.GaussianCost(0.5, y, lf.IdentityLinkFunction()).native()
+    assert (c.cost_id, c.link_id, c.closed_form, c.observation_noise) == (nat.COST_GAUSSIAN, nat.LINK_IDENTITY, 1, 0.5)
+    assert costs.GaussianCost(0.5, y, lf.SquareLinkFunction()).native().closed_form == 0
+    assert costs.GaussianCost(0.5, y, lf.IdentityLinkFunction()).native(force_autograd=True).closed_form == 0
+    b = costs.BernoulliCost(y, lf.SigmoidLinkFunction(jitter=1e-8))
+    assert b.y_train.dtype == torch.double and b.native().link_jitter == 1e-8 and b.native().closed_form == 1
+    mm = costs.MultiModalCost(0.4, 1.5, 0.3, y, lf.IdentityLinkFunction()).native()
+    assert (mm.shift, mm.bernoulli_noise, mm.closed_form) == (1.5, 0.3, 0)
+    st = costs.StudentTCost(4.0, y, lf.IdentityLinkFunction(), scale=0.7).native()
+    assert (st.degrees_of_freedom, st.scale, st.closed_form) == (4.0, 0.7, 1)
+    # the probit constant follows the default dtype at call time, as link_functions.py:42 does
+    torch.set_default_dtype(torch.float64)
+    try:
+        assert abs(costs.BernoulliCost(y, lf.ProbitLinkFunction()).native().probit_divisor - 2.0**0.5) < 5e-16
+    finally:
+        torch.set_default_dtype(torch.float32)
+    assert abs(costs.BernoulliCost(y, lf.ProbitLinkFunction()).native().probit_divisor - 1.4142135381698608) < 1e-15
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "projected_langevin_sampling_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.replace("pls_oracle", "oracle") or "import oracle" not in text, f
+                assert not re.search(r"^\s*(from|import)\s+oracle", text, flags=re.M), f
+
+
+def test_shard_ranges_partition():
+    from projected_langevin_sampling_b200.distributed import GridPlacement, shard_range
+
+    for total, world, align in [(4096, 8, 2), (1000, 3, 2), (1_000_000, 4, 128), (7, 8, 1), (20_000_000, 2, 128)]:
+        pieces = [shard_range(total, r, world, align) for r in range(world)]
+        assert pieces[0][0] == 0 and pieces[-1][1] == total
+        for (a, b), (c, d) in zip(pieces, pieces[1:]):
+            assert b == c and a <= b
+        assert all(b % align == 0 for _, b in pieces[:-1])
+    g = GridPlacement(rank=5, world=8, n_groups=2, j_groups=4)
+    assert (g.n_index, g.j_index) == (1, 1) and g.row_group_ranks() == [1, 5]
+    assert g.rows(20_000_000) == (10_000_000, 20_000_000) and g.particles(16384) == (4096, 8192)
+    with pytest.raises(ValueError):
+        GridPlacement(rank=0, world=8, n_groups=3, j_groups=2)
+
+
+GLOO_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["PLS_ROOT"])
+from projected_langevin_sampling_b200.distributed import GridPlacement, gradient_allreduce, make_row_group, shard_range
+dist.init_process_group("gloo", rank=int(os.environ["RANK"]), world_size=int(os.environ["WORLD_SIZE"]))
+rank, world = dist.get_rank(), dist.get_world_size()
+# (a) particle sharding: every rank owns a slice, slices tile [0, J), no communication needed for the update itself
+j0, j1 = shard_range(1001, rank, world, align=2)
+sizes = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+dist.all_gather(sizes, torch.tensor([j1 - j0]))
+assert sum(int(s) for s in sizes) == 1001
+# (b) row sharding: 2 x 1 grid, the (M, J_local) gradient is summed over the row group
+place = GridPlacement(rank=rank, world=world, n_groups=2, j_groups=1)
+hook = gradient_allreduce(make_row_group(place))
+g = torch.full((4, 6), float(rank + 1), dtype=torch.float64)
+hook(g)
+assert torch.equal(g, torch.full((4, 6), 3.0, dtype=torch.float64)), g
+r0, r1 = place.rows(1000)
+assert (r0, r1) == ((0, 512) if rank == 0 else (512, 1000))
+dist.barrier(); dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_gloo_world_size_2(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(GLOO_WORKER)
+    env = dict(os.environ, PLS_ROOT=ROOT, MASTER_ADDR="127.0.0.1", MASTER_PORT="29617", WORLD_SIZE="2")
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r)), stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
