@@ -79,6 +79,11 @@ typedef struct pls_cost {
   double scale;
   double link_jitter;
   double probit_divisor;
+  /* multimodal only: log(bernoulli_noise), log(1 - bernoulli_noise) and log(sqrt(2 pi s^2)) as the reference forms them
+   * (multimodal.py:55-72 builds them with torch.tensor(...) in the default dtype at call time) */
+  double log_weight_1;
+  double log_weight_2;
+  double log_normaliser;
 } pls_cost;
 
 /* ---- context ------------------------------------------------------------------------------------------------ */

@@ -303,8 +303,9 @@ class Cost:
             s2 = self.observation_noise**2
             e1 = y - mu + self.shift
             e2 = y - mu
-            a1 = math.log(self.bernoulli_noise) - 0.5 * e1 * e1 / s2
-            a2 = math.log(1 - self.bernoulli_noise) - 0.5 * e2 * e2 / s2
+            # the reference's log-weights are torch tensors in the default dtype (multimodal.py:66-72)
+            a1 = float(torch.log(torch.tensor(self.bernoulli_noise))) - 0.5 * e1 * e1 / s2
+            a2 = float(torch.log(torch.tensor(1 - self.bernoulli_noise))) - 0.5 * e2 * e2 / s2
             w = torch.softmax(torch.stack([a1, a2]), dim=0)
             return -(w[0] * e1 + w[1] * e2) / s2 * dmu
         raise ValueError(self.kind)

@@ -40,6 +40,9 @@ class PlsCost(C.Structure):
         ("scale", C.c_double),
         ("link_jitter", C.c_double),
         ("probit_divisor", C.c_double),
+        ("log_weight_1", C.c_double),
+        ("log_weight_2", C.c_double),
+        ("log_normaliser", C.c_double),
     ]
 
 

@@ -67,9 +67,8 @@ __device__ __forceinline__ double cost_value(const pls_cost& c, double y, double
       const double s2 = c.observation_noise * c.observation_noise;
       const double e1 = y - mu + c.shift;
       const double e2 = y - mu;
-      const double lognorm = log(sqrt(2.0 * 3.141592653589793238 * s2));
-      const double a1 = log(c.bernoulli_noise) + (-0.5 * (e1 * e1 / s2) - lognorm);
-      const double a2 = log(1.0 - c.bernoulli_noise) + (-0.5 * (e2 * e2 / s2) - lognorm);
+      const double a1 = c.log_weight_1 + (-0.5 * (e1 * e1 / s2) - c.log_normaliser);
+      const double a2 = c.log_weight_2 + (-0.5 * (e2 * e2 / s2) - c.log_normaliser);
       const double mx = fmax(a1, a2);
       return -(mx + log(exp(a1 - mx) + exp(a2 - mx)));
     }
@@ -108,8 +107,8 @@ __device__ __forceinline__ double cost_derivative(const pls_cost& c, double y, d
       const double s2 = c.observation_noise * c.observation_noise;
       const double e1 = y - mu + c.shift;
       const double e2 = y - mu;
-      const double a1 = log(c.bernoulli_noise) - 0.5 * e1 * e1 / s2;
-      const double a2 = log(1.0 - c.bernoulli_noise) - 0.5 * e2 * e2 / s2;
+      const double a1 = c.log_weight_1 - 0.5 * e1 * e1 / s2;
+      const double a2 = c.log_weight_2 - 0.5 * e2 * e2 / s2;
       const double mx = fmax(a1, a2);
       const double w1 = exp(a1 - mx), w2 = exp(a2 - mx);
       return -((w1 * e1 + w2 * e2) / (w1 + w2)) / s2 * dmu;

@@ -45,6 +45,7 @@ class PLSCost(ABC):
         c.shift, c.bernoulli_noise, c.degrees_of_freedom, c.scale = 0.0, 0.5, 1.0, 1.0
         c.link_jitter = float(getattr(link, "jitter", 0.0))
         c.probit_divisor = ProbitLinkFunction.divisor()
+        c.log_weight_1 = c.log_weight_2 = c.log_normaliser = 0.0
         self._extra_native_fields(c)
         return c
 

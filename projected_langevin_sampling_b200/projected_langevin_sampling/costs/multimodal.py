@@ -24,6 +24,11 @@ class MultiModalCost(PLSCost):
     def _extra_native_fields(self, c: nat.PlsCost) -> None:
         c.shift = float(self.shift)
         c.bernoulli_noise = float(self.bernoulli_noise)
+        # the reference builds these constants as torch tensors in the DEFAULT dtype at call time (multimodal.py:55-72);
+        # under a float32 default they are float32-rounded, and that rounding is part of its result
+        c.log_weight_1 = float(torch.log(torch.tensor(self.bernoulli_noise)))
+        c.log_weight_2 = float(torch.log(torch.tensor(1 - self.bernoulli_noise)))
+        c.log_normaliser = float(torch.log(torch.sqrt(2 * torch.tensor([torch.pi]) * (self.observation_noise**2))))
 
     def predict(self, prediction_samples: torch.Tensor) -> None:
         return None
