@@ -1,0 +1,464 @@
+#!/usr/bin/env python
+"""bench.py -- particle-updates/sec of the fused PLS Langevin step (BASELINE.json metric) on N B200s.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c4|c3|c2]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+A "step" is one Langevin step over all J particles of the workload:
+  C4 (default, the configuration the metric is quoted on): N=1,000,000 D=8 ARD, M=1024, J=4096, Gaussian cost.
+At --gpus N the particles are sharded (weak scaling: every GPU advances its own J particles against replicated
+X, y, Z, V~, lambda; no per-step communication; Philox noise keyed on the global particle index).
+
+The JSON line carries: value (device-timed, inputs resident in HBM), e2e (through the reference-facing API with pinned
+HOST buffers, copies inside the timed region), roofline (FP64 tensor, live CUDA-event kernel timing), cpu_baseline
+(the oracle's reference-style torch-CPU step on the box's host cores, bounded sample), clocks, gpu_launches.
+
+`--impl reference` times the reference's own CPU formulation of the path (the oracle port -- the reference itself needs
+gpytorch, which is not installed) on all host threads and prints the same line shape with "impl": "reference".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "PLS particle-updates/sec at N=1M,M=1024,J=4096; % of FP64/HBM roofline"
+UNIT = "particle-updates/s"
+
+WORKLOADS = {
+    # name: (N, D, M, J, cost)
+    "c4": dict(n=1_000_000, d=8, m=1024, j=4096, cost="gaussian", label="C4 UCI-scale synthetic regression N=1M D=8 ARD M=1024 J=4096"),
+    "c3": dict(n=100_000, d=1, m=256, j=4096, cost="poisson", label="C3 Poisson f^2 regression N=100k D=1 M=256 J=4096"),
+    "c2": dict(n=10_000, d=1, m=64, j=1024, cost="bernoulli", label="C2 1D Bernoulli classification N=10k M=64 J=1024"),
+}
+
+
+def synth(workload: dict, seed: int = 0):
+    """Synthetic inputs of SURVEY.md section 8(d), generated on the CPU generator (seed 0) in float64."""
+    g = torch.Generator().manual_seed(seed)
+    n, d, m = workload["n"], workload["d"], workload["m"]
+    if workload["cost"] == "gaussian":
+        x = torch.randn(n, d, generator=g, dtype=torch.float64)
+        ls = torch.tensor([math.sqrt(d) * (0.75 + 0.5 * k / max(d - 1, 1)) for k in range(d)], dtype=torch.float64)
+        y = torch.sin(x.sum(1) / math.sqrt(d)) + 0.1 * torch.randn(n, generator=g, dtype=torch.float64)
+        outputscale = 1.0
+    else:
+        x = torch.linspace(-3, 3, n, dtype=torch.float64).reshape(-1, 1)
+        ls = torch.tensor([0.5], dtype=torch.float64)
+        curve = 2.0 * torch.sin(1.5 * x.reshape(-1))
+        if workload["cost"] == "bernoulli":
+            y = torch.bernoulli(torch.sigmoid(curve), generator=g).double()
+        else:
+            y = torch.poisson(curve**2, generator=g).double()
+        outputscale = 1.0
+    z_idx = torch.arange(m) if workload["cost"] == "gaussian" else torch.linspace(0, n - 1, m).long()
+    return x, y, x[z_idx].clone(), ls, outputscale
+
+
+def make_pls(workload: dict, x, y, z, ls, outputscale):
+    import projected_langevin_sampling_b200 as pkg
+    from projected_langevin_sampling_b200.projected_langevin_sampling import costs, link_functions as lf
+
+    kernel = pkg.ScaleKernel(pkg.RBFKernel(ard_num_dims=x.shape[1], lengthscale=ls), outputscale=outputscale)
+    basis = pkg.OrthonormalBasis(pkg.PLSKernel(kernel, z), z, x, eigenvalue_threshold=workload.get("threshold", 0.0), verbose=False)
+    if workload["cost"] == "gaussian":
+        cost = costs.GaussianCost(observation_noise=0.01, y_train=y, link_function=lf.IdentityLinkFunction())
+    elif workload["cost"] == "bernoulli":
+        cost = costs.BernoulliCost(y_train=y, link_function=lf.SigmoidLinkFunction())
+    else:
+        cost = costs.PoissonCost(y_train=y, link_function=lf.SquareLinkFunction())
+    return pkg.PLS(basis, cost)
+
+
+# ---- clocks ------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi samples (200 ms) of SM clock and throttle reasons DURING the timed region."""
+
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index: int):
+        self.device_index = device_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.device_index}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, power, reasons = [], None, [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax = float(parts[1])
+                power.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, flag in zip(names, parts[3:7]):
+                if flag.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax, "power_w_max": max(power) if power else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---- CPU baseline (oracle port of the reference's CPU path) -----------------------------------------------------------
+def cpu_reference_sample(workload: dict, steps: int, warmup: int):
+    """The reference-style torch-CPU Langevin step (oracle.pls_oracle.reference_style_cpu_step: left-to-right dense
+    matmuls with the N x M Gram cached, eigh(eye) + torch.normal per step) on a bounded sample: a 1/20 row slice at full
+    M with J_c = 256 particles.  The J-independent products (k(X,Z) V~ and V~^T k(Z,X), which the reference re-forms
+    every step) and the J-dependent rest are timed separately and scaled linearly to the full N and J."""
+    from oracle.pls_oracle import OrthonormalBasisOracle, RBFScaleKernel, langevin_noise
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_default_dtype(torch.float64)
+    x, y, z, ls, outputscale = synth(workload)
+    n_full, j_full = workload["n"], workload["j"]
+    n_s = max(min(n_full, 1000), n_full // 20)
+    j_c = min(256, j_full)
+    xs, ys = x[:n_s], y[:n_s]
+    basis = OrthonormalBasisOracle(RBFScaleKernel(ls, outputscale), z, xs)
+    k_zx, vt, lam = basis.k_zx.contiguous(), basis.scaled_eigenvectors, basis.eigenvalues
+    p = torch.randn(vt.shape[1], j_c, generator=torch.Generator().manual_seed(1))
+    eta = 1e-9
+    t_fixed, t_rest = [], []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        phi = k_zx.T @ vt  # (N_s, M_k): re-formed by the reference every step (orthonormal.py:106-108)
+        back = (-eta * vt.T) @ k_zx  # (M_k, N_s): likewise (orthonormal.py:151-154)
+        t1 = time.perf_counter()
+        f = phi @ p
+        if workload["cost"] == "gaussian":
+            dc = (1 / 0.01) * (f - ys[:, None])
+        elif workload["cost"] == "bernoulli":
+            pr = torch.clip(torch.reciprocal(1 + torch.exp(-f)), 1e-10, 1 - 1e-10)
+            dc = -ys[:, None] * (1 - pr) + (1 - ys[:, None]) * pr
+        else:
+            dc = -2 * ys[:, None] / f + 2 * f
+        xi = langevin_noise(p.shape[0], j_c)  # eigh(eye(M_k)) + torch.normal, as samplers.py:27-35
+        delta = back @ dc - eta * torch.diag(torch.reciprocal(lam)) @ p + math.sqrt(2 * eta) * xi
+        p = p + delta
+        t2 = time.perf_counter()
+        if it >= warmup:
+            t_fixed.append(t1 - t0)
+            t_rest.append(t2 - t1)
+    scale_n = n_full / n_s
+    tf, tr = statistics.median(t_fixed), statistics.median(t_rest)
+    t_step_full = scale_n * (tf + tr * (j_full / j_c))
+    return {
+        "value": j_full / t_step_full,
+        "unit": UNIT,
+        "cores": torch.get_num_threads(),
+        "kind": "port",
+        "sample": (f"oracle port of the reference torch-CPU step, dense Gram cached, rows {n_s}/{n_full} at full M={workload['m']}, "
+                   f"J_c={j_c}: J-independent products {tf:.3f}s + J-dependent {tr:.3f}s per sampled step, scaled linearly to "
+                   f"N={n_full}, J={j_full} ({steps} timed steps, median)"),
+        "sample_seconds": sum(t_fixed) + sum(t_rest),
+        "ms_per_step_extrapolated": t_step_full * 1e3,
+    }
+
+
+def run_reference_arm(args, workload):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    t0 = time.perf_counter()
+    res = cpu_reference_sample(workload, steps=args.steps, warmup=args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": res["ms_per_step_extrapolated"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload["label"], "note": "CPU arm: one host, all threads; value extrapolated from the bounded sample"},
+        "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": time.perf_counter() - t0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---- FP64 peak -----------------------------------------------------------------------------------------------------------
+def measure_fp64_peak(n: int = 8192, reps: int = 6) -> float:
+    """cuBLAS DGEMM n^3 via torch.matmul, best of `reps` (TFLOP/s): the FP64 denominator MEASURED_PEAKS.json lacks."""
+    a = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    b = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    c = torch.empty_like(a)
+    torch.matmul(a, b, out=c)
+    torch.cuda.synchronize()
+    best = float("inf")
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(a, b, out=c)
+        e1.record()
+        e1.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    del a, b, c
+    return 2.0 * n**3 / best * 1e-9
+
+
+# ---- kernel timing hooks ----------------------------------------------------------------------------------------------------
+class KernelTimer:
+    """CUDA-event pairs around every forward / backward launch of the generated-operand GEMM (on torch's current stream,
+    which is the stream the library launches on)."""
+
+    def __init__(self):
+        self.records = []  # (kind, flops, e0, e1)
+        self.enabled = False
+
+    def install(self):
+        from projected_langevin_sampling_b200 import ops
+
+        timer = self
+        orig_fwd, orig_bwd = ops.forward, ops.backward
+
+        def fwd(ctx, kernel_id, xa, za, d, w, j, epilogue, out, cost=None, y=None):
+            if not timer.enabled:
+                return orig_fwd(ctx, kernel_id, xa, za, d, w, j, epilogue, out, cost=cost, y=y)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = orig_fwd(ctx, kernel_id, xa, za, d, w, j, epilogue, out, cost=cost, y=y)
+            e1.record()
+            timer.records.append(("forward", 2.0 * xa.shape[0] * za.shape[0] * j, e0, e1))
+            return r
+
+        def bwd(ctx, kernel_id, za, xa, d, dc, j, gp, splits, accumulate):
+            if not timer.enabled:
+                return orig_bwd(ctx, kernel_id, za, xa, d, dc, j, gp, splits, accumulate)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = orig_bwd(ctx, kernel_id, za, xa, d, dc, j, gp, splits, accumulate)
+            e1.record()
+            timer.records.append(("backward", 2.0 * xa.shape[0] * za.shape[0] * j, e0, e1))
+            return r
+
+        ops.forward, ops.backward = fwd, bwd
+
+    def summary(self):
+        out = {}
+        for kind in ("forward", "backward"):
+            recs = [r for r in self.records if r[0] == kind]
+            if recs:
+                ms = sum(r[2].elapsed_time(r[3]) for r in recs)
+                fl = sum(r[1] for r in recs)
+                out[kind] = {"launches": len(recs), "ms_total": ms, "tflops": fl / ms * 1e-9, "flops_per_launch": fl / len(recs),
+                             "ms_per_launch": ms / len(recs)}
+        recs = self.records
+        ms = sum(r[2].elapsed_time(r[3]) for r in recs)
+        fl = sum(r[1] for r in recs)
+        out["both"] = {"launches": len(recs), "ms_total": ms, "tflops": fl / ms * 1e-9 if ms > 0 else 0.0}
+        return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", type=str, default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", type=str, default="c4", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--n", type=int, default=None, help="override N (debugging; the line then names the reduced workload)")
+    ap.add_argument("--j", type=int, default=None)
+    args = ap.parse_args()
+    workload = dict(WORKLOADS[args.workload])
+    if args.n or args.j:
+        workload["n"] = args.n or workload["n"]
+        workload["j"] = args.j or workload["j"]
+        workload["label"] += f" [OVERRIDDEN to N={workload['n']} J={workload['j']}: not the named config]"
+    args.warmup = max(args.warmup, 0)
+
+    if args.impl == "reference":
+        run_reference_arm(args, workload)
+        return
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the PLS hot path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from projected_langevin_sampling_b200 import _native
+
+    ctx = _native.context()
+    t_setup = time.perf_counter()
+    x, y, z, ls, outputscale = synth(workload)
+    pls = make_pls(workload, x, y, z, ls, outputscale)
+    m_k = pls.basis.approximation_dimension
+    j_local = workload["j"]  # weak scaling: every GPU owns J particles
+    j_off = rank * j_local
+    lam_min = float(pls.basis.eigenvalues.min())
+    eta = 1e-9 if workload["cost"] == "gaussian" else 1e-6
+    particles = pls.initialise_particles(j_local, seed=1000 + rank)
+    torch.cuda.synchronize()
+    setup_s = time.perf_counter() - t_setup
+
+    timer = KernelTimer()
+    timer.install()
+    seed = 2024
+    step_no = 0
+    for _ in range(max(args.warmup, 3)):
+        pls.step_(particles, eta, philox=(seed, step_no, j_off))
+        step_no += 1
+    torch.cuda.synchronize()
+
+    # ---- device-resident timed region -------------------------------------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    launches0 = ctx.launches
+    timer.enabled = True
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        pls.step_(particles, eta, philox=(seed, step_no, j_off))
+        step_no += 1
+    e1.record()
+    torch.cuda.synchronize()
+    timer.enabled = False
+    if dist is not None:
+        dist.barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = ctx.launches - launches0
+    clocks = sampler.stop()
+    finite = bool(torch.isfinite(particles).all())
+    if dist is not None:
+        t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_per_step = ms_total / args.steps
+    value = workload["j"] * world * args.steps / (ms_total * 1e-3)
+    ksum = timer.summary()
+
+    # ---- end-to-end through the reference-facing API with pinned host buffers ------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        p_host = particles.cpu().pin_memory()
+        d_host = torch.empty_like(p_host).pin_memory()
+        torch.set_default_dtype(torch.float64)  # the reference's noise draw is in the default dtype (README.md:86-87)
+        torch.manual_seed(7)
+        e2e_steps = max(1, min(args.steps, 3))
+
+        def e2e_step():
+            p_dev = p_host.to("cuda", non_blocking=True)  # H2D: particles
+            delta = pls.calculate_particle_update(p_dev, eta)  # draws xi on the host generator + H2D, as the reference
+            d_host.copy_(delta, non_blocking=True)  # D2H: the step's result
+            torch.cuda.synchronize()
+            p_host.add_(d_host)
+
+        e2e_step()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        torch.set_default_dtype(torch.float32)
+        nbytes = m_k * j_local * 8
+        e2e = {"value": workload["j"] * world * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": 2 * nbytes,
+               "d2h_bytes_per_step": nbytes, "steps": e2e_steps, "ms_per_step": dt / e2e_steps * 1e3,
+               "what": "PLS.calculate_particle_update(particles, step_size) with particles in pinned host memory: H2D particles, "
+                       "host torch.normal noise + H2D (the reference's stream), fused step, D2H delta, host add"}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline / baselines (rank 0) -----------------------------------------------------------------------------------------
+    peak_live = measure_fp64_peak()
+    peak_file = None
+    try:
+        peak_file = json.load(open(os.path.join(ROOT, "profiles", "fp64_peak_r01.json")))["fp64_tflops_sustained"]
+    except Exception:
+        pass
+    peak = peak_file or peak_live
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get(args.workload)
+    except Exception:
+        pass
+    n, m, j = workload["n"], workload["m"], workload["j"]
+    achieved = ksum["both"]["tflops"]
+    roofline = {
+        "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
+        "traffic": traffic,
+        "kernel": "pls::gen_gemm_kernel (forward + backward roles; FP64 DMMA.8x8x4, no tcgen05 kind exists for f64)",
+        "algorithmic_flops_per_step": 4.0 * n * m * j,
+        "per_role": {k: ksum[k] for k in ("forward", "backward") if k in ksum},
+        "kernel_share_of_step": ksum["both"]["ms_total"] / ms_total if world == 1 else None,
+        "peak_source": ("cuBLAS DGEMM via torch.matmul fp64 8192^3 measured on this pool's B200 "
+                        f"(profiles/fp64_peak_r01.json sustained={peak_file}, live best-of-6 in this run={peak_live:.2f}); "
+                        "MEASURED_PEAKS.json holds no FP64 figure; FP64 pipe peak from tools/fp64_microbench = 37.1 TFLOP/s"),
+        "step_tflops": 4.0 * n * m * j / (ms_per_step * 1e-3) * 1e-12,
+    }
+    cpu = None
+    if not args.no_cpu_baseline:
+        r = cpu_reference_sample(workload, steps=2, warmup=1)
+        cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": workload["label"], "N": n, "D": workload["d"], "M": m, "M_k": m_k, "J_per_gpu": j,
+                   "J_global": j * world, "cost": workload["cost"], "step_size": eta, "lambda_min": lam_min,
+                   "noise": "Philox4x32-10 on device keyed on global (row, particle)", "parallelism": f"particle-sharded x{world}",
+                   "l2": "per-step working set (Dc chunk 8 GiB written+read) exceeds the 126 MB L2; no flush needed",
+                   "particles_finite": finite, "setup_s": setup_s},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
