@@ -30,6 +30,7 @@ namespace pls {
 namespace {
 
 constexpr int SMEM_HEADER = 128;  // mbarriers
+constexpr int NWARPS = NTHREADS / 32;
 
 // The cost functors are called (not inlined) from the tile epilogue: 64 calls per thread per 128 x 128 x K tile is
 // noise next to the main loop, and it keeps the kernel's code small.
@@ -89,8 +90,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gen_gemm_kernel(const GenGemmPara
   for (int i = tid; i < STAGES * BK * SB + STAGES * BK * sp; i += NTHREADS) sB[i] = 0.0;
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full[s], 1);
-      mbar_init(&empty[s], NTHREADS / 32);
+      mbar_init(&full[s], NWARPS);
+      mbar_init(&empty[s], NWARPS);
     }
     fence_mbar_init();
   }
@@ -112,16 +113,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) gen_gemm_kernel(const GenGemmPara
   }
 
   const int64_t cw = (p.ldb - j0 < BJ) ? (p.ldb - j0) : BJ;  // columns copied per row (ldb even => 16-byte multiple)
+  // Every warp's lane 0 issues its share of a stage (rows warp, warp + 8, ... of the streamed tile; warp 0 adds the point
+  // rows) and posts the bytes it issued on the stage's full barrier (8 arrivals), so no single warp carries the copy
+  // issue cost on its critical path.
   auto issue = [&](int c) {
     const int stage = c % STAGES;
     const int64_t k0 = begin + (int64_t)c * BK;
     const int kc = (int)((end - k0 < BK) ? (end - k0) : BK);
     uint64_t* bar = &full[stage];
-    mbar_expect_tx(bar, (uint32_t)(kc * (cw * 8 + sp * 8)));
+    const int my_rows = (kc > warp) ? ((kc - warp + NWARPS - 1) / NWARPS) : 0;
+    uint32_t bytes = (uint32_t)(my_rows * cw * 8);
+    if (warp == 0) bytes += (uint32_t)(kc * sp * 8);
+    mbar_expect_tx(bar, bytes);
     double* dst = sB + stage * BK * SB;
     const double* src = p.b + k0 * p.ldb + j0;
-    for (int r = 0; r < kc; ++r) bulk_g2s(dst + r * SB, src + (int64_t)r * p.ldb, (uint32_t)(cw * 8), bar);
-    bulk_g2s(sP + stage * BK * sp, p.red_aug + k0 * sp, (uint32_t)(kc * sp * 8), bar);
+    for (int r = warp; r < kc; r += NWARPS) bulk_g2s(dst + r * SB, src + (int64_t)r * p.ldb, (uint32_t)(cw * 8), bar);
+    if (warp == 0) bulk_g2s(sP + stage * BK * sp, p.red_aug + k0 * sp, (uint32_t)(kc * sp * 8), bar);
   };
 
   double acc[2][16][2];
@@ -133,7 +140,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gen_gemm_kernel(const GenGemmPara
       acc[h][nt][1] = 0.0;
     }
 
-  if (tid == 0) {
+  if (lane == 0) {
     for (int c = 0; c < STAGES - 1 && c < nchunks; ++c) issue(c);
   }
 
@@ -196,10 +203,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) gen_gemm_kernel(const GenGemmPara
       }
     }
     __syncwarp();
-    if (lane == 0) mbar_arrive(&empty[stage]);
-    if (tid == 0) {
-      // refill the stage consumed in iteration c-1 with chunk c + STAGES - 1 (every warp has long left it, so the
-      // wait does not stall the issuing warp; the copy has one full chunk of compute to land)
+    if (lane == 0) {
+      mbar_arrive(&empty[stage]);
+      // refill the stage consumed in iteration c-1 with chunk c + STAGES - 1: every warp has long left that stage, so the
+      // wait does not stall, and the copies have one full chunk of compute to land
       const int cn = c + STAGES - 1;
       if (cn < nchunks) {
         mbar_wait(&empty[cn % STAGES], (((uint32_t)(cn / STAGES)) & 1u) ^ 1u);
