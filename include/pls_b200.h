@@ -173,13 +173,19 @@ int pls_energy_terms_f64(pls_ctx* ctx, const double* partial, int64_t tiles, int
 int pls_philox_normal_f64(pls_ctx* ctx, uint64_t seed, uint64_t step, int64_t rows, int64_t j,
                           int64_t j_global_offset, double* out, int64_t ldo, void* stream);
 
+/* out[i] = exp(x[i]) with the exponent routine the kernels use for Gram entries: fast != 0 is the table-driven
+ * branch-free variant of the hot loop (csrc/pls_common.cuh gram_exp_fast), fast == 0 the CUDA library exp used by the
+ * dense Gram and the selector.  Exposed so the tests can bound the hot loop's exponent error in ulps. */
+int pls_gram_exp_f64(pls_ctx* ctx, const double* x, int64_t n, int fast, double* out, void* stream);
+
 /* ---- ConditionalVariance inducing-point selector ------------------------------------------------------------- */
 /* Greedy pivoted Cholesky (src/inducing_point_selectors/conditional_variance.py:27-120) on the ALREADY PERMUTED
  * points xp_aug (augmented layout, n rows; the numpy permutation of :60 stays on the host).
  *   kdiag: the value diag k(x, x) takes (outputscale for RBF -- exact, as gpytorch returns it), ignored for LINEAR
  *          where the diagonal is computed;
  *   ci: workspace (m-1) x n doubles; di: workspace n doubles; scratch: workspace pls_cv_scratch_doubles(n) doubles;
- *   indices_out: m int64 (positions in the permuted order; entries never reached keep the sentinel n, as :63);
+ *   indices_out: m int64 in DEVICE memory, pre-filled by the caller with the sentinel n (as :63); receives positions in
+ *          the permuted order, entries never reached keep the sentinel;
  *   n_selected_out (host int*): how many entries were filled.  Synchronises the stream before returning. */
 int64_t pls_cv_scratch_doubles(int64_t n);
 int pls_cv_select_f64(pls_ctx* ctx, int kernel_id, const double* xp_aug, int64_t n, int d, double kdiag, int m,

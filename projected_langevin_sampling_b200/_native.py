@@ -76,6 +76,7 @@ SIGNATURES = {
     "pls_cost_value_f64": (_int, [_vp, _costp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp]),
     "pls_energy_terms_f64": (_int, [_vp, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _vp, _vp]),
     "pls_philox_normal_f64": (_int, [_vp, _u64, _u64, _i64, _i64, _i64, _vp, _i64, _vp]),
+    "pls_gram_exp_f64": (_int, [_vp, _vp, _i64, _int, _vp, _vp]),
     "pls_cv_scratch_doubles": (_i64, [_i64]),
     "pls_cv_select_f64": (_int, [_vp, _int, _vp, _i64, _int, _dbl, _int, _dbl, _dbl, _int, _vp, _vp, _vp, _vp, C.POINTER(_int), _vp]),
 }

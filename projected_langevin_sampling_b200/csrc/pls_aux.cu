@@ -71,6 +71,20 @@ cudaError_t launch_gram(int kernel_id, const double* ra, int64_t nr, const doubl
   return cudaGetLastError();
 }
 
+__global__ void gram_exp_kernel(const double* __restrict__ x, int64_t n, int fast, double* __restrict__ out) {
+  __shared__ double tbl[64];
+  if (threadIdx.x < 64) tbl[threadIdx.x] = kExp2Table[threadIdx.x];
+  __syncthreads();
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = fast ? gram_exp_fast(x[i], tbl) : gram_exp(x[i]);
+}
+
+cudaError_t launch_gram_exp(const double* x, int64_t n, int fast, double* out, cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  gram_exp_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(x, n, fast, out);
+  return cudaGetLastError();
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // Philox4x32-10 + Box-Muller
 // ---------------------------------------------------------------------------------------------------------------

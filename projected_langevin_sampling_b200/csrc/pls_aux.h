@@ -47,6 +47,8 @@ cudaError_t launch_cost_value(const pls_cost& cost, const double* y, const doubl
 cudaError_t launch_energy_terms(const double* partial, int64_t tiles, int64_t ldpart, const double* p, int64_t ldp,
                                 int64_t m_k, const double* inv_lambda, int64_t j, double* out, cudaStream_t stream);
 
+cudaError_t launch_gram_exp(const double* x, int64_t n, int fast, double* out, cudaStream_t stream);
+
 // ConditionalVariance selector (pls_selector.cu)
 int64_t cv_scratch_doubles(int64_t n);
 cudaError_t run_cv_select(const pls_ctx* ctx, int kernel_id, const double* xp_aug, int64_t n, int d, double kdiag, int m,

@@ -29,13 +29,13 @@ namespace pls {
 
 namespace {
 
-constexpr int SMEM_HEADER = 128;  // mbarriers
+constexpr int SMEM_HEADER = 128 + 64 * 8;  // mbarriers + exp table
 constexpr int NWARPS = NTHREADS / 32;
 
 // The cost functors are called (not inlined) from the tile epilogue: 64 calls per thread per 128 x 128 x K tile is
 // noise next to the main loop, and it keeps the kernel's code small.
-__device__ __noinline__ double cost_derivative_call(const pls_cost& c, double y, double f) { return cost_derivative(c, y, f); }
-__device__ __noinline__ double cost_value_call(const pls_cost& c, double y, double f) { return cost_value(c, y, f); }
+static __device__ __noinline__ double cost_derivative_call(const pls_cost& c, double y, double f) { return cost_derivative(c, y, f); }
+static __device__ __noinline__ double cost_value_call(const pls_cost& c, double y, double f) { return cost_value(c, y, f); }
 
 __host__ __device__ inline size_t gen_gemm_smem_bytes(int sp) {
   return SMEM_HEADER + sizeof(double) * (size_t)(STAGES * BK * SB + STAGES * BK * sp);
@@ -46,6 +46,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gen_gemm_kernel(const GenGemmPara
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
   uint64_t* empty = full + STAGES;
+  double* sExp = reinterpret_cast<double*>(smem_raw + 128);        // 2^(j/64)
   double* sB = reinterpret_cast<double*>(smem_raw + SMEM_HEADER);  // [STAGES][BK][SB]
   double* sP = sB + STAGES * BK * SB;                              // [STAGES][BK][sp]
 
@@ -88,6 +89,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gen_gemm_kernel(const GenGemmPara
   // ---- one-time setup -------------------------------------------------------------------------------------------
   // zero the staging buffers: rows never written by a copy (reduction tail) must hold finite values
   for (int i = tid; i < STAGES * BK * SB + STAGES * BK * sp; i += NTHREADS) sB[i] = 0.0;
+  if (tid < 64) sExp[tid] = kExp2Table[tid];
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], NWARPS);
@@ -147,10 +149,46 @@ __global__ void __launch_bounds__(NTHREADS, 1) gen_gemm_kernel(const GenGemmPara
   const bool rbf = (p.kernel_id == PLS_KERNEL_RBF);
 
   // ---- main loop over reduction chunks ----------------------------------------------------------------------------
+  // Software-pipelined at half-group granularity: while the 32 DMMAs of one k4 step (one reduction point per thread)
+  // are issued, the Gram values of the NEXT k4 step are generated (S DMMAs + exp), so the latency of the exponent chain
+  // hides behind this warp's own tensor work instead of relying on the other warp of the scheduler.
+  auto exponent_tile = [&](const double* Pt, int grp, double& s00, double& s01, double& s10, double& s11) {
+    // S (16 rows x 8 points) = rows . points^T over the augmented coordinates
+    s00 = 0.0; s01 = 0.0; s10 = 0.0; s11 = 0.0;
+    const double* prow = Pt + (grp * 8 + g) * sp;
+#pragma unroll
+    for (int kd = 0; kd < NKD; ++kd) {
+      const double b2 = prow[pcol[kd]];
+      dmma(s00, s01, a2[0][kd], b2);
+      dmma(s10, s11, a2[1][kd], b2);
+    }
+  };
+  auto gram_value = [&](double s, bool valid) {
+    const double v = rbf ? gram_exp_fast(s, sExp) : s;
+    return valid ? v : 0.0;
+  };
+  auto mma_step = [&](const double* brow, double ka, double kb) {
+#pragma unroll
+    for (int pr = 0; pr < 8; ++pr) {
+      const double2 bv = *reinterpret_cast<const double2*>(brow + 16 * pr);
+      dmma(acc[0][2 * pr][0], acc[0][2 * pr][1], ka, bv.x);
+      dmma(acc[1][2 * pr][0], acc[1][2 * pr][1], kb, bv.x);
+      dmma(acc[0][2 * pr + 1][0], acc[0][2 * pr + 1][1], ka, bv.y);
+      dmma(acc[1][2 * pr + 1][0], acc[1][2 * pr + 1][1], kb, bv.y);
+    }
+  };
+
+  double s00, s01, s10, s11;  // exponents of the group in flight
+  double k0a = 0.0, k0b = 0.0;  // Gram values of k4 step 0 (point 2t) for rows g, g+8
+  if (nchunks > 0) {
+    mbar_wait(&full[0], 0u);
+    const int kc0 = (int)((end - begin < BK) ? (end - begin) : BK);
+    exponent_tile(sP, 0, s00, s01, s10, s11);
+    k0a = gram_value(s00, 2 * t < kc0);
+    k0b = gram_value(s10, 2 * t < kc0);
+  }
   for (int c = 0; c < nchunks; ++c) {
     const int stage = c % STAGES;
-    mbar_wait(&full[stage], ((uint32_t)(c / STAGES)) & 1u);
-
     const int64_t k0 = begin + (int64_t)c * BK;
     const int kc = (int)((end - k0 < BK) ? (end - k0) : BK);
     const int ngroups = (kc + 7) >> 3;
@@ -159,48 +197,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) gen_gemm_kernel(const GenGemmPara
 
 #pragma unroll 1
     for (int grp = 0; grp < ngroups; ++grp) {
-      // S (16 rows x 8 points) = rows . points^T over the augmented coordinates
-      double s00 = 0.0, s01 = 0.0, s10 = 0.0, s11 = 0.0;
-      const double* prow = Pt + (grp * 8 + g) * sp;
-#pragma unroll
-      for (int kd = 0; kd < NKD; ++kd) {
-        const double b2 = prow[pcol[kd]];
-        dmma(s00, s01, a2[0][kd], b2);
-        dmma(s10, s11, a2[1][kd], b2);
-      }
-      if (rbf) {
-        s00 = gram_exp(s00);
-        s01 = gram_exp(s01);
-        s10 = gram_exp(s10);
-        s11 = gram_exp(s11);
-      }
       const int p0 = grp * 8 + 2 * t;  // this thread's two reduction points: p0 (k4 step 0) and p0 + 1 (k4 step 1)
-      if (p0 >= kc) {
-        s00 = 0.0;
-        s10 = 0.0;
-      }
-      if (p0 + 1 >= kc) {
-        s01 = 0.0;
-        s11 = 0.0;
-      }
       const double* b0 = Bt + p0 * SB + 2 * g;
-#pragma unroll
-      for (int pr = 0; pr < 8; ++pr) {
-        const double2 bv = *reinterpret_cast<const double2*>(b0 + 16 * pr);
-        dmma(acc[0][2 * pr][0], acc[0][2 * pr][1], s00, bv.x);
-        dmma(acc[1][2 * pr][0], acc[1][2 * pr][1], s10, bv.x);
-        dmma(acc[0][2 * pr + 1][0], acc[0][2 * pr + 1][1], s00, bv.y);
-        dmma(acc[1][2 * pr + 1][0], acc[1][2 * pr + 1][1], s10, bv.y);
+      // k4 step 0 with (k0a, k0b); meanwhile the Gram values of step 1
+      const double k1a = gram_value(s01, p0 + 1 < kc);
+      const double k1b = gram_value(s11, p0 + 1 < kc);
+      mma_step(b0, k0a, k0b);
+      // k4 step 1 with (k1a, k1b); meanwhile exponents + step-0 Gram values of the next group (possibly next chunk)
+      if (grp + 1 < ngroups) {
+        exponent_tile(Pt, grp + 1, s00, s01, s10, s11);
+        k0a = gram_value(s00, p0 + 8 < kc);
+        k0b = gram_value(s10, p0 + 8 < kc);
+      } else if (c + 1 < nchunks) {
+        const int nstage = (c + 1) % STAGES;
+        mbar_wait(&full[nstage], ((uint32_t)((c + 1) / STAGES)) & 1u);
+        const int64_t nk0 = k0 + BK;
+        const int nkc = (int)((end - nk0 < BK) ? (end - nk0) : BK);
+        exponent_tile(sP + nstage * BK * sp, 0, s00, s01, s10, s11);
+        k0a = gram_value(s00, 2 * t < nkc);
+        k0b = gram_value(s10, 2 * t < nkc);
       }
-      const double* b1 = b0 + SB;
-#pragma unroll
-      for (int pr = 0; pr < 8; ++pr) {
-        const double2 bv = *reinterpret_cast<const double2*>(b1 + 16 * pr);
-        dmma(acc[0][2 * pr][0], acc[0][2 * pr][1], s01, bv.x);
-        dmma(acc[1][2 * pr][0], acc[1][2 * pr][1], s11, bv.x);
-        dmma(acc[0][2 * pr + 1][0], acc[0][2 * pr + 1][1], s01, bv.y);
-        dmma(acc[1][2 * pr + 1][0], acc[1][2 * pr + 1][1], s11, bv.y);
-      }
+      mma_step(b0 + SB, k1a, k1b);
     }
     __syncwarp();
     if (lane == 0) {

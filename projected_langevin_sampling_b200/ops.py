@@ -162,6 +162,14 @@ def philox_normal(ctx: nat.Context, seed: int, step: int, rows: int, j: int, j_g
     return out
 
 
+def gram_exp(ctx: nat.Context, x: torch.Tensor, fast: bool) -> torch.Tensor:
+    """exp(x) with the hot loop's table-driven routine (fast=True) or the CUDA library exp (fast=False)."""
+    out = torch.empty_like(x)
+    ctx.check(ctx.lib.pls_gram_exp_f64(ctx.handle, x.data_ptr(), x.numel(), int(fast), out.data_ptr(), ctx.stream()))
+    ctx.launches += 1
+    return out
+
+
 def cv_select(ctx: nat.Context, kernel_id: int, xp_aug: torch.Tensor, d: int, kdiag: float, m: int, jitter: float,
               threshold: Optional[float]) -> Tuple[torch.Tensor, int]:
     """Returns (indices into the permuted order (m,), number selected)."""

@@ -1,0 +1,108 @@
+"""GPU unit tests of individual C-ABI entry points (called through the ctypes binding): the hot loop's exponent routine,
+the small DGEMM, the split reduction, direct forward/backward calls with leading dimensions."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from projected_langevin_sampling_b200 import _native
+
+    return _native.context()
+
+
+def _ulps(got: torch.Tensor, want: torch.Tensor) -> torch.Tensor:
+    spacing = torch.from_numpy(np.spacing(want.cpu().numpy())).to(want.device)
+    return (got - want).abs() / spacing
+
+
+def test_hot_loop_exp_within_two_ulps(ctx):
+    from projected_langevin_sampling_b200 import ops
+
+    g = torch.Generator().manual_seed(0)
+    x = torch.cat([
+        -700.0 * torch.rand(2_000_000, generator=g, dtype=torch.float64),  # the Gram exponent's range
+        10.0 * torch.rand(200_000, generator=g, dtype=torch.float64) - 5.0,
+        torch.tensor([0.0, -1e-300, -1e-17, -0.5, -1.0, -36.04365338911715, -699.999, 1.0, 2.302585092994046]),
+    ]).cuda()
+    fast = ops.gram_exp(ctx, x, fast=True)
+    lib = ops.gram_exp(ctx, x, fast=False)
+    want = torch.exp(x.cpu().to(torch.float64)).cuda()  # torch CPU exp as the third opinion
+    assert _ulps(lib, want).max().item() <= 1.0
+    assert _ulps(fast, want).max().item() <= 2.0
+    assert _ulps(fast, want).mean().item() < 0.5
+    assert ops.gram_exp(ctx, torch.tensor([0.0], dtype=torch.float64).cuda(), fast=True).item() == 1.0
+    # clamped below -700: tiny but finite, never NaN
+    tail = ops.gram_exp(ctx, torch.tensor([-1e4, -1e8, -float("inf")], dtype=torch.float64).cuda(), fast=True)
+    assert torch.isfinite(tail).all() and (tail < 1e-300).all() and (tail >= 0).all()
+
+
+@pytest.mark.parametrize("rows,k,j,trans", [(64, 64, 64, False), (100, 37, 130, False), (33, 200, 77, True), (1, 5, 3, True)])
+def test_small_gemm_matches_torch(ctx, rows, k, j, trans):
+    from projected_langevin_sampling_b200 import ops
+
+    g = torch.Generator().manual_seed(rows + k + j)
+    a = torch.randn((k, rows) if trans else (rows, k), generator=g, dtype=torch.float64).cuda()
+    b = torch.randn(k, j, generator=g, dtype=torch.float64).cuda()
+    out = torch.zeros(rows, j + 3, dtype=torch.float64).cuda()  # leading dimension > j
+    ops.gemm(ctx, a, b, out[:, :j], trans_a=trans)
+    want = (a.T if trans else a).cpu() @ b.cpu()
+    assert (out[:, :j].cpu() - want).abs().max().item() <= 1e-12 * max(1.0, want.abs().max().item())
+    assert (out[:, j:] == 0).all()  # nothing written outside the logical matrix
+
+
+def test_forward_backward_direct_calls_with_leading_dimensions(ctx):
+    """pls_forward_f64 / pls_backward_f64 / pls_reduce_splits_f64 called directly, against dense torch algebra on the
+    Gram matrix the library itself produces with pls_gram_f64."""
+    from projected_langevin_sampling_b200 import _native as nat, ops
+
+    g = torch.Generator().manual_seed(11)
+    n, m, d, j = 700, 90, 5, 150
+    x = torch.randn(n, d, generator=g, dtype=torch.float64).cuda()
+    z = torch.randn(m, d, generator=g, dtype=torch.float64).cuda()
+    inv_ls = [0.5, 0.4, 0.3, 0.6, 0.7]
+    centre = z.mean(0).tolist()
+    xa = ops.prepare_points(ctx, nat.KERNEL_RBF, x, inv_ls, centre, 0.0)
+    za = ops.prepare_points(ctx, nat.KERNEL_RBF, z, inv_ls, centre, float(np.log(1.7)))
+    k_xz = ops.gram(ctx, nat.KERNEL_RBF, xa, za, d)  # (n, m), includes the outputscale
+    dense = 1.7 * torch.exp(-0.5 * (((x[:, None, :] - z[None, :, :]) * torch.tensor(inv_ls, dtype=torch.float64).cuda()) ** 2).sum(-1))
+    assert (k_xz - dense).abs().max().item() < 1e-13
+    ldw = 160
+    w_store = torch.randn(m, ldw, generator=g, dtype=torch.float64).cuda()
+    f_store = torch.full((n, 156), -7.0, dtype=torch.float64).cuda()
+    ops.forward(ctx, nat.KERNEL_RBF, xa, za, d, w_store, j, nat.EPI_PREDICTION, f_store)
+    want_f = k_xz @ w_store[:, :j]
+    assert (f_store[:, :j] - want_f).abs().max().item() < 1e-11
+    assert (f_store[:, j:] == -7.0).all()
+    dc_store = torch.randn(n, 152, generator=g, dtype=torch.float64).cuda()
+    for splits in (1, 3, 7):
+        gp = torch.full((splits, m, 154), 5.0, dtype=torch.float64).cuda()
+        ops.backward(ctx, nat.KERNEL_RBF, za, xa, d, dc_store, j, gp, splits, accumulate=False)
+        out = torch.empty(m, 154, dtype=torch.float64).cuda()
+        ops.reduce_splits(ctx, gp, j, out)
+        want_g = k_xz.T @ dc_store[:, :j]
+        assert (out[:, :j] - want_g).abs().max().item() < 1e-10 * want_g.abs().max().item()
+        ops.backward(ctx, nat.KERNEL_RBF, za, xa, d, dc_store, j, gp, splits, accumulate=True)  # += doubles it
+        ops.reduce_splits(ctx, gp, j, out)
+        assert (out[:, :j] - 2 * want_g).abs().max().item() < 1e-10 * want_g.abs().max().item()
+        assert (gp[:, :, j:] == 5.0).all()
+
+
+def test_argument_errors_are_reported_not_thrown(ctx):
+    from projected_langevin_sampling_b200 import _native as nat
+
+    w = torch.zeros(4, 5, dtype=torch.float64).cuda()  # odd leading dimension: rejected by the streamed-operand contract
+    out = torch.zeros(8, 6, dtype=torch.float64).cuda()
+    xa = torch.zeros(8, 4, dtype=torch.float64).cuda()
+    za = torch.zeros(4, 4, dtype=torch.float64).cuda()
+    rc = ctx.lib.pls_forward_f64(ctx.handle, nat.KERNEL_RBF, xa.data_ptr(), 8, za.data_ptr(), 4, 1, w.data_ptr(), 5, 5,
+                                 nat.EPI_PREDICTION, None, None, out.data_ptr(), 6, ctx.stream())
+    assert rc != 0 and b"even ldw" in ctx.lib.pls_last_error(ctx.handle)
+    rc = ctx.lib.pls_forward_f64(ctx.handle, 9, xa.data_ptr(), 8, za.data_ptr(), 4, 1, w.data_ptr(), 6, 5,
+                                 nat.EPI_PREDICTION, None, None, out.data_ptr(), 6, ctx.stream())
+    assert rc != 0 and b"unknown kernel_id" in ctx.lib.pls_last_error(ctx.handle)
+    with pytest.raises(nat.NativeLibraryError):
+        ctx.check(rc)
