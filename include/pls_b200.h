@@ -48,7 +48,7 @@ enum { PLS_LINK_IDENTITY = 0, PLS_LINK_SIGMOID = 1, PLS_LINK_PROBIT = 2, PLS_LIN
 enum {
   PLS_EPI_PREDICTION = 0,      /* F = k(X,Z) W                      (n x J)        orthonormal.py:98-108            */
   PLS_EPI_COST_DERIVATIVE = 1, /* d_2 c(y, F)                       (n x J)        PLS.calculate_cost_derivative    */
-  PLS_EPI_COST = 2             /* per 128-row tile: sum_n c(y_n,F)  (tiles x J)    PLS.calculate_cost               */
+  PLS_EPI_COST = 2             /* per row tile: sum_n c(y_n,F)      (tiles x J)    PLS.calculate_cost               */
 };
 /* Langevin noise source for pls_project_update_f64 */
 enum {
@@ -101,6 +101,13 @@ int pls_point_stride(int d);
 /* number of N-splits pls_backward_f64 wants for an (m x j) gradient reduced over n_rows training rows */
 int pls_backward_splits(const pls_ctx* ctx, int64_t n_rows, int64_t m, int64_t j);
 
+/* rows per forward tile for a launch over j particle columns: the row granularity of the PLS_EPI_COST partial sums
+ * (64 for the 64 x 256 tile, 128 for the 128 x 128 tile used when j <= 128) */
+int pls_forward_tile_rows(const pls_ctx* ctx, int64_t j);
+/* force the CTA tile shape of pls_forward_f64 / pls_backward_f64: rt = 1 (64 rows x 256 particles), 2 (128 x 128),
+ * 0 = choose per launch (default).  Benchmarks and tests only; the environment variable PLS_B200_TILE_RT does the same. */
+void pls_set_tile_shape(pls_ctx* ctx, int rt);
+
 /* ---- one-time setup ------------------------------------------------------------------------------------------ */
 /* Builds the augmented layout of a point set.  x: n x d (ldx).  inv_lengthscale, centre: HOST arrays of d doubles
  * (ignored for PLS_KERNEL_LINEAR).  c_extra is added to the c entry (log(outputscale) for the inducing set, 0 for
@@ -124,7 +131,7 @@ int pls_gemm_f64(pls_ctx* ctx, int trans_a, const double* a, int64_t lda, const 
 /* Forward contraction with on-the-fly Gram tiles: for training rows [0, n) of xa,
  *   F[n][j] = sum_m k(x_n, z_m) W[m][j],      W = V~ P  (m x j, ldw, ldw even, 16-byte aligned)
  * and the epilogue selected by `epilogue`.  y (n doubles) and cost are read for the cost epilogues only.
- * out: n x j (ldo) for PREDICTION / COST_DERIVATIVE (ldo even, 16-byte aligned), ceil(n/128) x j (ldo) for COST.
+ * out: n x j (ldo) for PREDICTION / COST_DERIVATIVE (ldo even, 16-byte aligned), ceil(n / pls_forward_tile_rows(ctx, j)) x j (ldo) for COST.
  * Replaces OrthonormalBasis.calculate_untransformed_train_prediction_samples (pls/basis/orthonormal.py:98-108) fused
  * with <Cost>.calculate_cost_derivative / calculate_cost (pls/costs/*.py); the N x M Gram is never materialised. */
 int pls_forward_f64(pls_ctx* ctx, int kernel_id, const double* xa, int64_t n, const double* za, int64_t m, int d,

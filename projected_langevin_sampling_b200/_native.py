@@ -22,7 +22,7 @@ LINK_IDENTITY, LINK_SIGMOID, LINK_PROBIT, LINK_SQUARE = range(4)
 EPI_PREDICTION, EPI_COST_DERIVATIVE, EPI_COST = range(3)
 NOISE_NONE, NOISE_GIVEN, NOISE_PHILOX = range(3)
 ABI_VERSION = 1
-TILE_ROWS = 128  # rows per forward tile (PLS_EPI_COST partial layout)
+COST_VALUE_TILE_ROWS = 128  # rows per partial sum of pls_cost_value_f64 (dense F)
 
 
 class PlsCost(C.Structure):
@@ -61,6 +61,8 @@ SIGNATURES = {
     "pls_last_error": (C.c_char_p, [_vp]),
     "pls_sm_count": (_int, [_vp]),
     "pls_point_stride": (_int, [_int]),
+    "pls_forward_tile_rows": (_int, [_vp, _i64]),
+    "pls_set_tile_shape": (None, [_vp, _int]),
     "pls_backward_splits": (_int, [_vp, _i64, _i64, _i64]),
     "pls_prepare_points_f64": (_int, [_vp, _int, _vp, _i64, _int, _i64, C.POINTER(_dbl), C.POINTER(_dbl), _dbl, _vp, _vp]),
     "pls_gram_f64": (_int, [_vp, _int, _vp, _i64, _vp, _i64, _int, _vp, _i64, _vp]),

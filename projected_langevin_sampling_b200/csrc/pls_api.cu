@@ -2,6 +2,7 @@
 // dispatch to the kernels.  Nothing here allocates device memory or synchronises (except pls_cv_select_f64).
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "pls_aux.h"
@@ -66,6 +67,7 @@ int pls_ctx_create(int device, pls_ctx** out) {
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
   c->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+  if (const char* env = getenv("PLS_B200_TILE_RT")) c->tile_rt = atoi(env);
   *out = c;
   return 0;
 }
@@ -85,7 +87,9 @@ int pls_backward_splits(const pls_ctx* ctx, int64_t n_rows, int64_t m, int64_t j
   // Enough CTAs for >= 8 waves of one CTA per SM, a whole number of waves when possible, and splits no shorter than
   // 16 pipeline chunks.
   const int sms = (ctx && ctx->sm_count > 0) ? ctx->sm_count : 148;
-  const int64_t tiles = ((m + pls::BR - 1) / pls::BR) * ((j + pls::BJ - 1) / pls::BJ);
+  const int rt = pls::choose_tile_rt(ctx, j);
+  const int64_t br = pls::tile_rows(rt), bj = pls::tile_cols(rt);
+  const int64_t tiles = ((m + br - 1) / br) * ((j + bj - 1) / bj);
   if (tiles <= 0 || n_rows <= 0) return 1;
   const int64_t chunks = (n_rows + pls::BK - 1) / pls::BK;
   int64_t max_splits = chunks / 16;
@@ -107,6 +111,12 @@ int pls_backward_splits(const pls_ctx* ctx, int64_t n_rows, int64_t m, int64_t j
   }
   if (best > 4096) best = 4096;
   return (int)best;
+}
+
+int pls_forward_tile_rows(const pls_ctx* ctx, int64_t j) { return pls::tile_rows(pls::choose_tile_rt(ctx, j)); }
+
+void pls_set_tile_shape(pls_ctx* ctx, int rt) {
+  if (ctx) ctx->tile_rt = (rt == 1 || rt == 2) ? rt : 0;
 }
 
 int pls_prepare_points_f64(pls_ctx* ctx, int kernel_id, const double* x, int64_t n, int d, int64_t ldx,
@@ -165,6 +175,7 @@ int pls_forward_f64(pls_ctx* ctx, int kernel_id, const double* xa, int64_t n, co
   }
   p.rows_aug = xa; p.n_rows = n; p.red_aug = za; p.red_total = m; p.b = w; p.ldb = ldw; p.j = j;
   p.sp = pls::point_stride(d); p.d = d; p.kernel_id = kernel_id; p.epilogue = epilogue; p.splits = 1; p.accumulate = 0;
+  p.rt = pls::choose_tile_rt(ctx, j);
   p.out = out; p.ldo = ldo; p.y = y;
   return check_cuda(ctx, pls::launch_gen_gemm_forward(ctx, p, (cudaStream_t)stream), "pls_forward_f64");
 }
@@ -180,7 +191,7 @@ int pls_backward_f64(pls_ctx* ctx, int kernel_id, const double* za, int64_t m, c
   pls::GenGemmParams p{};
   p.rows_aug = za; p.n_rows = m; p.red_aug = xa; p.red_total = n; p.b = dc; p.ldb = lddc; p.j = j;
   p.sp = pls::point_stride(d); p.d = d; p.kernel_id = kernel_id; p.epilogue = -1; p.splits = splits;
-  p.accumulate = accumulate; p.out = gp; p.ldo = ldg; p.y = nullptr;
+  p.accumulate = accumulate; p.out = gp; p.ldo = ldg; p.y = nullptr; p.rt = pls::choose_tile_rt(ctx, j);
   return check_cuda(ctx, pls::launch_gen_gemm_backward(ctx, p, (cudaStream_t)stream), "pls_backward_f64");
 }
 

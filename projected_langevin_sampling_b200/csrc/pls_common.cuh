@@ -9,13 +9,15 @@
 namespace pls {
 
 // ---- tiling of the generated-operand GEMM (pls_gen_gemm.cu) -----------------------------------------------------
-constexpr int BR = 128;        // output rows per CTA: 8 warps x 16 rows (two m8 DMMA row tiles per warp)
-constexpr int BJ = 128;        // output columns (particles) per CTA: 16 n8 DMMA column tiles per warp
+// CTA tile: 8 warps, each RT m8 row tiles x 32/RT n8 column tiles (64 fp64 accumulators per thread either way).
+//   RT = 1: 64 rows x 256 particles (default: a generated Gram element is reused across 256 columns)
+//   RT = 2: 128 rows x 128 particles (particle slices of <= 128 columns)
+__host__ __device__ constexpr int tile_rows(int rt) { return 64 * rt; }
+__host__ __device__ constexpr int tile_cols(int rt) { return 256 / rt; }
 constexpr int BK = 32;         // reduction points per pipeline stage (4 groups of 8)
 constexpr int STAGES = 3;      // bulk-copy pipeline depth
-constexpr int SB = BJ + 2;     // smem row stride (doubles) of the streamed tile: conflict-free LDS.128 fragments
-constexpr int NTHREADS = 256;  // 8 warps, 1 CTA / SM (64 fp64 accumulators per thread)
-constexpr int MAX_NKD = 7;     // D + 2 <= 28
+constexpr int NTHREADS = 256;  // 8 warps, 1 CTA / SM
+constexpr int MAX_NKD = 7;     // ceil(D / 4) with D <= 26
 
 __host__ __device__ inline int point_stride(int d) {
   // smallest SP >= d + 2 with SP % 8 == 4: rows of SP doubles make the B-fragment reads of the point tile
@@ -25,13 +27,13 @@ __host__ __device__ inline int point_stride(int d) {
   while (sp < need) sp += 8;
   return sp;
 }
-__host__ __device__ inline int point_ksteps(int d) { return (d + 2 + 3) / 4; }
+__host__ __device__ inline int point_ksteps(int d) { return (d + 3) / 4; }  // exponent DMMAs per 8 x 8 tile: coordinates only
 
 // ---- DMMA ------------------------------------------------------------------------------------------------------
 // D(8x8) += A(8x4) * B(4x8), fp64.  Fragment layout (lane = 4*g + t): a = A[g][t], b = B[t][g],
 // c0 = C[g][2t], c1 = C[g][2t+1].
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1},{%2},{%3},{%0,%1};"
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1},{%2},{%3},{%0,%1};"
                : "+d"(c0), "+d"(c1)
                : "d"(a), "d"(b));
 }
@@ -101,7 +103,8 @@ __device__ __constant__ double kExp2Table[64] = {
 // Max error ~1 ulp (table entry 0.5 ulp + polynomial/rounding), checked against exp() in tests/test_gpu_kernels.py.
 // Inputs below -700 are clamped (result ~1e-304 instead of an underflowed 0: irrelevant at any Gram scale).
 __device__ __forceinline__ double gram_exp_fast(double x, const double* __restrict__ tbl) {
-  x = fmax(x, -700.0);
+  // clamp on the ALU (compare of the high word), not on the FP64 pipe
+  if ((unsigned)__double2hiint(x) >= 0xC085E000u) x = -700.0;
   const double t = fma(x, 92.33248261689366, 6755399441055744.0);  // 64/ln2, 1.5 * 2^52: integer part lands in the low word
   const int k = __double2loint(t);
   const double kf = t - 6755399441055744.0;

@@ -5,33 +5,30 @@
 namespace pls {
 
 #define PLS_DECL(k) \
-  cudaError_t launch_gen_gemm_nkd##k(bool backward, const pls_ctx* ctx, const GenGemmParams& p, int64_t grid, cudaStream_t stream);
+  cudaError_t launch_gen_gemm_nkd##k(bool backward, const pls_ctx* ctx, const GenGemmParams& p, cudaStream_t stream);
 PLS_DECL(1) PLS_DECL(2) PLS_DECL(3) PLS_DECL(4) PLS_DECL(5) PLS_DECL(6) PLS_DECL(7)
 #undef PLS_DECL
 
-static cudaError_t dispatch(bool backward, const pls_ctx* ctx, const GenGemmParams& p, int64_t grid, cudaStream_t stream) {
-  if (grid <= 0) return cudaSuccess;
-  if (grid > 2147483647LL) return cudaErrorInvalidConfiguration;
+static cudaError_t dispatch(bool backward, const pls_ctx* ctx, const GenGemmParams& p, cudaStream_t stream) {
+  if (p.rt != 1 && p.rt != 2) return cudaErrorInvalidValue;
   switch (point_ksteps(p.d)) {
-    case 1: return launch_gen_gemm_nkd1(backward, ctx, p, grid, stream);
-    case 2: return launch_gen_gemm_nkd2(backward, ctx, p, grid, stream);
-    case 3: return launch_gen_gemm_nkd3(backward, ctx, p, grid, stream);
-    case 4: return launch_gen_gemm_nkd4(backward, ctx, p, grid, stream);
-    case 5: return launch_gen_gemm_nkd5(backward, ctx, p, grid, stream);
-    case 6: return launch_gen_gemm_nkd6(backward, ctx, p, grid, stream);
-    case 7: return launch_gen_gemm_nkd7(backward, ctx, p, grid, stream);
+    case 1: return launch_gen_gemm_nkd1(backward, ctx, p, stream);
+    case 2: return launch_gen_gemm_nkd2(backward, ctx, p, stream);
+    case 3: return launch_gen_gemm_nkd3(backward, ctx, p, stream);
+    case 4: return launch_gen_gemm_nkd4(backward, ctx, p, stream);
+    case 5: return launch_gen_gemm_nkd5(backward, ctx, p, stream);
+    case 6: return launch_gen_gemm_nkd6(backward, ctx, p, stream);
+    case 7: return launch_gen_gemm_nkd7(backward, ctx, p, stream);
     default: return cudaErrorInvalidValue;
   }
 }
 
 cudaError_t launch_gen_gemm_forward(const pls_ctx* ctx, const GenGemmParams& p, cudaStream_t stream) {
-  const int64_t tiles = ((p.n_rows + BR - 1) / BR) * ((p.j + BJ - 1) / BJ);
-  return dispatch(false, ctx, p, tiles, stream);
+  return dispatch(false, ctx, p, stream);
 }
 
 cudaError_t launch_gen_gemm_backward(const pls_ctx* ctx, const GenGemmParams& p, cudaStream_t stream) {
-  const int64_t tiles = ((p.n_rows + BR - 1) / BR) * ((p.j + BJ - 1) / BJ);
-  return dispatch(true, ctx, p, tiles * p.splits, stream);
+  return dispatch(true, ctx, p, stream);
 }
 
 }  // namespace pls

@@ -8,19 +8,23 @@
 //                  -> G'[m][j] = sum_n k(z_m, x_n) Dc[n][j]                        (orthonormal.py:151-155)
 //
 // Design (B200, sm_100a):
-//   * FP64 has no tcgen05 kind; the FP64 tensor instruction is DMMA.8x8x4 and it shares one 64-FMA/clk/SM pipe with
-//     DFMA (measured, profiles/fp64_microbench_r01.txt), so every FP64 op spent on generating K is taken from the
-//     GEMM.  The tile is therefore as wide in J as the register file allows (128 x 128 fp64 accumulators = half the
-//     SM's registers) and each K element is generated exactly once per CTA: warp w owns rows [16w, 16w+16) and ALL
-//     128 columns, so the A fragments it needs are the ones it generates, in registers, with no shared-memory round
-//     trip and no __syncthreads in the main loop.
-//   * the exponent tile itself is a DMMA: rows and reduction points are stored "augmented"
-//     ([x~ | c | 1] . [z~ | 1 | c']), so S = A2 * B2^T gives -|x~ - z~|^2/2 + log(sigma^2) directly in C-fragment
-//     layout; the thread that holds S[g][2t], S[g][2t+1] uses them as the A fragments of two k4 steps whose k index
-//     t maps to reduction points 2t and 2t+1 (the B rows are addressed accordingly), so no shuffle is needed either.
+//   * FP64 has no tcgen05 kind; the FP64 tensor instruction is DMMA.8x8x4 (every wider PTX f64 mma shape lowers to it)
+//     and it shares one 64-FMA/clk/SM pipe with DFMA (measured, profiles/fp64_microbench_r01.txt), so every FP64 op
+//     spent on generating K is taken from the GEMM.  A generated K element costs ~4*ceil(D/4) FMA slots of exponent
+//     DMMA + ~10 slots of exp and is reused across the BJ columns of the tile, so the tile is as WIDE in J as the
+//     register file allows: 64 fp64 accumulators per thread (half the SM's registers) arranged as RT row tiles x
+//     32/RT column tiles per warp.  RT = 1 -> CTA tile 64 rows x 256 particles (generation overhead ~18/256),
+//     RT = 2 -> 128 x 128 (~18/128; kept for narrow particle slices).  Warp w owns rows [8 RT w, 8 RT (w+1)) and ALL
+//     columns, so the A fragments it needs are the ones it generates, in registers: no shared-memory round trip and
+//     no __syncthreads in the main loop.
+//   * the exponent tile itself is a DMMA: S = c_row + c_point + x~ . z~ (= -|x~ - z~|^2/2 + log sigma^2) comes out in
+//     C-fragment layout; the thread that holds S[g][2t], S[g][2t+1] uses exp of them as the A fragments of two k4
+//     steps whose k index t maps to reduction points 2t and 2t+1 (the B rows are addressed accordingly): no shuffle.
 //   * B (W or Dc rows) and the reduction-point rows are staged by the TMA engine (cp.async.bulk -> UBLKCP) through a
-//     3-stage mbarrier pipeline; one elected thread issues, all 8 warps consume; rows are padded to 130 doubles so the
-//     LDS.128 B-fragment reads are bank-conflict free.
+//     3-stage mbarrier pipeline; every warp's lane 0 issues a share, all 8 warps consume; rows are padded by 2 doubles
+//     so the LDS.128 B-fragment reads are bank-conflict free.
+//   * the loop over 8-point groups is flat and branch-free (kernel kind is a template parameter) so ptxas can interleave
+//     the exponent chain of the NEXT k4 step with the 32 DMMAs of the current one.
 #pragma once
 #include "pls_cost.cuh"
 #include "pls_internal.h"
@@ -32,17 +36,29 @@ namespace {
 constexpr int SMEM_HEADER = 128 + 64 * 8;  // mbarriers + exp table
 constexpr int NWARPS = NTHREADS / 32;
 
-// The cost functors are called (not inlined) from the tile epilogue: 64 calls per thread per 128 x 128 x K tile is
-// noise next to the main loop, and it keeps the kernel's code small.
+// The cost functors are called (not inlined) from the tile epilogue: 64 calls per thread per tile is noise next to the
+// main loop, and it keeps the kernel's code small.
 static __device__ __noinline__ double cost_derivative_call(const pls_cost& c, double y, double f) { return cost_derivative(c, y, f); }
 static __device__ __noinline__ double cost_value_call(const pls_cost& c, double y, double f) { return cost_value(c, y, f); }
 
+template <int RT>
+struct Tile {
+  static constexpr int NT = 32 / RT;          // n8 column tiles per warp
+  static constexpr int BR = tile_rows(RT);    // rows per CTA
+  static constexpr int BJ = tile_cols(RT);    // columns per CTA
+  static constexpr int SB = BJ + 2;           // smem row stride of the streamed tile
+  static constexpr int NPR = NT / 2;          // column pairs (one LDS.128 each)
+};
+
+template <int RT>
 __host__ __device__ inline size_t gen_gemm_smem_bytes(int sp) {
-  return SMEM_HEADER + sizeof(double) * (size_t)(STAGES * BK * SB + STAGES * BK * sp);
+  return SMEM_HEADER + sizeof(double) * (size_t)(STAGES * BK * Tile<RT>::SB + STAGES * BK * sp);
 }
 
-template <int NKD, bool BACKWARD>
+template <int NKD, bool BACKWARD, bool RBF, int RT>
 __global__ void __launch_bounds__(NTHREADS, 1) gen_gemm_kernel(const GenGemmParams p) {
+  using T = Tile<RT>;
+  constexpr int NT = T::NT, BR = T::BR, BJ = T::BJ, SB = T::SB, NPR = T::NPR;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
   uint64_t* empty = full + STAGES;
@@ -84,7 +100,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) gen_gemm_kernel(const GenGemmPara
     if (end > p.red_total) end = p.red_total;
     if (begin > end) begin = end;
   }
-  const int nchunks = (int)((end - begin + BK - 1) / BK);
+  const int red_len = (int)(end - begin);
+  const int nchunks = (red_len + BK - 1) / BK;
+  const int total_groups = (red_len + 7) >> 3;  // BK is a multiple of 8: groups never straddle chunks
 
   // ---- one-time setup -------------------------------------------------------------------------------------------
   // zero the staging buffers: rows never written by a copy (reduction tail) must hold finite values
@@ -100,18 +118,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) gen_gemm_kernel(const GenGemmPara
   fence_proxy_async();  // generic-proxy zero fill ordered before the async-proxy bulk copies
   __syncthreads();
 
-  // row-side exponent fragments (A operand of the S DMMA): rows g and g+8 of this warp's 16 rows
-  double a2[2][NKD];
-  int pcol[NKD];
+  // row-side exponent fragments (A operand of the S DMMA): row g of each of this warp's RT row tiles.  Coordinates only;
+  // the c entry (column d of the augmented row) seeds the accumulator together with the point's c.
+  double a2[RT][NKD];
+  double crow[RT];
 #pragma unroll
-  for (int kd = 0; kd < NKD; ++kd) {
-    const int dd = t + 4 * kd;
-    pcol[kd] = (dd == p.d) ? p.d + 1 : ((dd == p.d + 1) ? p.d : dd);  // reduction side swaps the c / 1 entries
+  for (int h = 0; h < RT; ++h) {
+    const int64_t r = row0 + (warp * RT + h) * 8 + g;
+    const bool rv = r < p.n_rows;
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int64_t r = row0 + warp * 16 + g + 8 * h;
-      a2[h][kd] = (r < p.n_rows) ? p.rows_aug[r * sp + dd] : 0.0;
+    for (int kd = 0; kd < NKD; ++kd) {
+      const int dd = t + 4 * kd;
+      a2[h][kd] = (rv && dd < p.d) ? p.rows_aug[r * sp + dd] : 0.0;
     }
+    crow[h] = rv ? p.rows_aug[r * sp + p.d] : 0.0;
   }
 
   const int64_t cw = (p.ldb - j0 < BJ) ? (p.ldb - j0) : BJ;  // columns copied per row (ldb even => 16-byte multiple)
@@ -133,11 +153,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) gen_gemm_kernel(const GenGemmPara
     if (warp == 0) bulk_g2s(sP + stage * BK * sp, p.red_aug + k0 * sp, (uint32_t)(kc * sp * 8), bar);
   };
 
-  double acc[2][16][2];
+  double acc[RT][NT][2];
 #pragma unroll
-  for (int h = 0; h < 2; ++h)
+  for (int h = 0; h < RT; ++h)
 #pragma unroll
-    for (int nt = 0; nt < 16; ++nt) {
+    for (int nt = 0; nt < NT; ++nt) {
       acc[h][nt][0] = 0.0;
       acc[h][nt][1] = 0.0;
     }
@@ -146,103 +166,105 @@ __global__ void __launch_bounds__(NTHREADS, 1) gen_gemm_kernel(const GenGemmPara
     for (int c = 0; c < STAGES - 1 && c < nchunks; ++c) issue(c);
   }
 
-  const bool rbf = (p.kernel_id == PLS_KERNEL_RBF);
-
-  // ---- main loop over reduction chunks ----------------------------------------------------------------------------
-  // Software-pipelined at half-group granularity: while the 32 DMMAs of one k4 step (one reduction point per thread)
-  // are issued, the Gram values of the NEXT k4 step are generated (S DMMAs + exp), so the latency of the exponent chain
-  // hides behind this warp's own tensor work instead of relying on the other warp of the scheduler.
-  auto exponent_tile = [&](const double* Pt, int grp, double& s00, double& s01, double& s10, double& s11) {
-    // S (16 rows x 8 points) = rows . points^T over the augmented coordinates
-    s00 = 0.0; s01 = 0.0; s10 = 0.0; s11 = 0.0;
-    const double* prow = Pt + (grp * 8 + g) * sp;
+  // ---- main loop over groups of 8 reduction points ------------------------------------------------------------------
+  // Software-pipelined at k4-step granularity: while the DMMAs of one k4 step (one reduction point per thread) are
+  // issued, the Gram values of the NEXT k4 step are generated (S DMMAs + exp), so the latency of the exponent chain
+  // hides behind this warp's own tensor work.
+  // exponents of group `grp` of the point tile Pt: S[h] (8 rows x 8 points) in C-fragment layout
+  auto exponent_tile = [&](const double* Pt, int grp, double (&s)[RT][2]) {
+    const double* prow = Pt + (grp * 8 + g) * sp;          // B fragment: point g of the group, coordinate t + 4 kd
+    const double* pc = Pt + (grp * 8 + 2 * t) * sp + p.d;  // c entries of this thread's two points
+    const double c0 = pc[0], c1 = pc[sp];
+#pragma unroll
+    for (int h = 0; h < RT; ++h) {
+      s[h][0] = crow[h] + c0;
+      s[h][1] = crow[h] + c1;
+    }
 #pragma unroll
     for (int kd = 0; kd < NKD; ++kd) {
-      const double b2 = prow[pcol[kd]];
-      dmma(s00, s01, a2[0][kd], b2);
-      dmma(s10, s11, a2[1][kd], b2);
+      const double b2 = prow[t + 4 * kd];
+#pragma unroll
+      for (int h = 0; h < RT; ++h) dmma(s[h][0], s[h][1], a2[h][kd], b2);
     }
   };
-  auto gram_value = [&](double s, bool valid) {
-    const double v = rbf ? gram_exp_fast(s, sExp) : s;
+  auto gram_value = [&](double sv, bool valid) {
+    const double v = RBF ? gram_exp_fast(sv, sExp) : sv;
     return valid ? v : 0.0;
   };
-  auto mma_step = [&](const double* brow, double ka, double kb) {
+  auto mma_step = [&](const double* brow, const double (&ka)[RT]) {
 #pragma unroll
-    for (int pr = 0; pr < 8; ++pr) {
+    for (int pr = 0; pr < NPR; ++pr) {
       const double2 bv = *reinterpret_cast<const double2*>(brow + 16 * pr);
-      dmma(acc[0][2 * pr][0], acc[0][2 * pr][1], ka, bv.x);
-      dmma(acc[1][2 * pr][0], acc[1][2 * pr][1], kb, bv.x);
-      dmma(acc[0][2 * pr + 1][0], acc[0][2 * pr + 1][1], ka, bv.y);
-      dmma(acc[1][2 * pr + 1][0], acc[1][2 * pr + 1][1], kb, bv.y);
+#pragma unroll
+      for (int h = 0; h < RT; ++h) {
+        dmma(acc[h][2 * pr][0], acc[h][2 * pr][1], ka[h], bv.x);
+        dmma(acc[h][2 * pr + 1][0], acc[h][2 * pr + 1][1], ka[h], bv.y);
+      }
     }
   };
 
-  double s00, s01, s10, s11;  // exponents of the group in flight
-  double k0a = 0.0, k0b = 0.0;  // Gram values of k4 step 0 (point 2t) for rows g, g+8
+  double s[RT][2];  // exponents of the group in flight
+  double k0[RT];    // Gram values of k4 step 0 (point 2t)
+#pragma unroll
+  for (int h = 0; h < RT; ++h) k0[h] = 0.0;
   if (nchunks > 0) {
     mbar_wait(&full[0], 0u);
-    const int kc0 = (int)((end - begin < BK) ? (end - begin) : BK);
-    exponent_tile(sP, 0, s00, s01, s10, s11);
-    k0a = gram_value(s00, 2 * t < kc0);
-    k0b = gram_value(s10, 2 * t < kc0);
+    exponent_tile(sP, 0, s);
+#pragma unroll
+    for (int h = 0; h < RT; ++h) k0[h] = gram_value(s[h][0], 2 * t < red_len);
   }
-  for (int c = 0; c < nchunks; ++c) {
-    const int stage = c % STAGES;
-    const int64_t k0 = begin + (int64_t)c * BK;
-    const int kc = (int)((end - k0 < BK) ? (end - k0) : BK);
-    const int ngroups = (kc + 7) >> 3;
-    const double* Bt = sB + stage * BK * SB;
-    const double* Pt = sP + stage * BK * sp;
-
 #pragma unroll 1
-    for (int grp = 0; grp < ngroups; ++grp) {
-      const int p0 = grp * 8 + 2 * t;  // this thread's two reduction points: p0 (k4 step 0) and p0 + 1 (k4 step 1)
-      const double* b0 = Bt + p0 * SB + 2 * g;
-      // k4 step 0 with (k0a, k0b); meanwhile the Gram values of step 1
-      const double k1a = gram_value(s01, p0 + 1 < kc);
-      const double k1b = gram_value(s11, p0 + 1 < kc);
-      mma_step(b0, k0a, k0b);
-      // k4 step 1 with (k1a, k1b); meanwhile exponents + step-0 Gram values of the next group (possibly next chunk)
-      if (grp + 1 < ngroups) {
-        exponent_tile(Pt, grp + 1, s00, s01, s10, s11);
-        k0a = gram_value(s00, p0 + 8 < kc);
-        k0b = gram_value(s10, p0 + 8 < kc);
-      } else if (c + 1 < nchunks) {
-        const int nstage = (c + 1) % STAGES;
-        mbar_wait(&full[nstage], ((uint32_t)((c + 1) / STAGES)) & 1u);
-        const int64_t nk0 = k0 + BK;
-        const int nkc = (int)((end - nk0 < BK) ? (end - nk0) : BK);
-        exponent_tile(sP + nstage * BK * sp, 0, s00, s01, s10, s11);
-        k0a = gram_value(s00, 2 * t < nkc);
-        k0b = gram_value(s10, 2 * t < nkc);
-      }
-      mma_step(b0 + SB, k1a, k1b);
-    }
-    __syncwarp();
-    if (lane == 0) {
-      mbar_arrive(&empty[stage]);
-      // refill the stage consumed in iteration c-1 with chunk c + STAGES - 1: every warp has long left that stage, so the
-      // wait does not stall, and the copies have one full chunk of compute to land
-      const int cn = c + STAGES - 1;
-      if (cn < nchunks) {
-        mbar_wait(&empty[cn % STAGES], (((uint32_t)(cn / STAGES)) & 1u) ^ 1u);
-        issue(cn);
+  for (int gi = 0; gi < total_groups; ++gi) {
+    const int c = gi >> 2;  // BK / 8 = 4 groups per chunk
+    const int grp = gi & 3;
+    const int stage = c % STAGES;
+    // the group after this one: the next chunk's stage must have landed before its exponents are formed
+    const int gn = (gi + 1 < total_groups) ? gi + 1 : gi;
+    const int cn = gn >> 2;
+    const int nstage = cn % STAGES;
+    if (cn != c) mbar_wait(&full[nstage], ((uint32_t)(cn / STAGES)) & 1u);
+
+    const int p0 = grp * 8 + 2 * t;  // this thread's two reduction points: p0 (k4 step 0) and p0 + 1 (k4 step 1)
+    const int pg = gi * 8 + 2 * t;   // ... counted from `begin`
+    const double* b0 = sB + (stage * BK + p0) * SB + 2 * g;
+    // k4 step 0 with k0; meanwhile the Gram values of step 1
+    double k1[RT];
+#pragma unroll
+    for (int h = 0; h < RT; ++h) k1[h] = gram_value(s[h][1], pg + 1 < red_len);
+    mma_step(b0, k0);
+    // k4 step 1 with k1; meanwhile exponents + step-0 Gram values of the next group
+    exponent_tile(sP + nstage * BK * sp, gn & 3, s);
+    const bool nvalid = (gn != gi) && (gn * 8 + 2 * t < red_len);
+#pragma unroll
+    for (int h = 0; h < RT; ++h) k0[h] = gram_value(s[h][0], nvalid);
+    mma_step(b0 + SB, k1);
+
+    if (grp == 3 || gi + 1 == total_groups) {  // chunk c fully consumed by this warp
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&empty[stage]);
+        // refill the stage consumed in chunk c-1 with chunk c + STAGES - 1: every warp has long left that stage, so the
+        // wait does not stall, and the copies have one full chunk of compute to land
+        const int cf = c + STAGES - 1;
+        if (cf < nchunks) {
+          mbar_wait(&empty[cf % STAGES], (((uint32_t)(cf / STAGES)) & 1u) ^ 1u);
+          issue(cf);
+        }
       }
     }
   }
 
   // ---- epilogue ---------------------------------------------------------------------------------------------------
   // Column map: thread (g,t) holds, for column pair pr, the 4 consecutive columns j0 + 16 pr + 4 t + {0,1,2,3} as
-  // acc[h][2pr][0], acc[h][2pr+1][0], acc[h][2pr][1], acc[h][2pr+1][1]; rows row0 + 16 warp + g + 8 h.
+  // acc[h][2pr][0], acc[h][2pr+1][0], acc[h][2pr][1], acc[h][2pr+1][1]; rows row0 + 8 (RT warp + h) + g.
   if (BACKWARD) {
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int64_t r = row0 + warp * 16 + g + 8 * h;
+    for (int h = 0; h < RT; ++h) {
+      const int64_t r = row0 + (warp * RT + h) * 8 + g;
       if (r >= p.n_rows) continue;
       double* orow = p.out + ((int64_t)split * p.n_rows + r) * p.ldo;
 #pragma unroll
-      for (int pr = 0; pr < 8; ++pr) {
+      for (int pr = 0; pr < NPR; ++pr) {
         const int64_t col = j0 + 16 * pr + 4 * t;
         double v[4] = {acc[h][2 * pr][0], acc[h][2 * pr + 1][0], acc[h][2 * pr][1], acc[h][2 * pr + 1][1]};
         if (col + 3 < p.j) {
@@ -268,25 +290,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) gen_gemm_kernel(const GenGemmPara
 
   if (p.epilogue == PLS_EPI_COST) {
     // per-column sum over this tile's rows of c(y_n, F[n][j]) -> out[rt][j]
-    double ysel[2];
-    bool rvalid[2];
+    double ysel[RT];
+    bool rvalid[RT];
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int64_t r = row0 + warp * 16 + g + 8 * h;
+    for (int h = 0; h < RT; ++h) {
+      const int64_t r = row0 + (warp * RT + h) * 8 + g;
       rvalid[h] = r < p.n_rows;
       ysel[h] = rvalid[h] ? p.y[r] : 0.0;
     }
     __syncthreads();  // every warp is done with the staging buffers; reuse stage 0 as reduction scratch
     double* sred = sB;  // [8 warps][BJ]
 #pragma unroll
-    for (int pr = 0; pr < 8; ++pr) {
+    for (int pr = 0; pr < NPR; ++pr) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int nt = 2 * pr + (e & 1);
         const int ce = e >> 1;
         double v = 0.0;
 #pragma unroll
-        for (int h = 0; h < 2; ++h)
+        for (int h = 0; h < RT; ++h)
           if (rvalid[h]) v += cost_value_call(p.cost, ysel[h], acc[h][nt][ce]);
         v += __shfl_xor_sync(0xffffffffu, v, 4);
         v += __shfl_xor_sync(0xffffffffu, v, 8);
@@ -298,7 +320,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gen_gemm_kernel(const GenGemmPara
     if (tid < BJ && j0 + tid < p.j) {
       double v = 0.0;
 #pragma unroll
-      for (int w = 0; w < NTHREADS / 32; ++w) v += sred[w * BJ + tid];
+      for (int w = 0; w < NWARPS; ++w) v += sred[w * BJ + tid];
       p.out[rt * p.ldo + j0 + tid] = v;
     }
     return;
@@ -306,13 +328,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) gen_gemm_kernel(const GenGemmPara
 
   const bool dcost = (p.epilogue == PLS_EPI_COST_DERIVATIVE);
 #pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    const int64_t r = row0 + warp * 16 + g + 8 * h;
+  for (int h = 0; h < RT; ++h) {
+    const int64_t r = row0 + (warp * RT + h) * 8 + g;
     if (r >= p.n_rows) continue;
     const double yv = dcost ? p.y[r] : 0.0;
     double* orow = p.out + r * p.ldo;
 #pragma unroll
-    for (int pr = 0; pr < 8; ++pr) {
+    for (int pr = 0; pr < NPR; ++pr) {
       const int64_t col = j0 + 16 * pr + 4 * t;
       double v[4] = {acc[h][2 * pr][0], acc[h][2 * pr + 1][0], acc[h][2 * pr][1], acc[h][2 * pr + 1][1]};
       if (dcost) {
@@ -332,14 +354,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) gen_gemm_kernel(const GenGemmPara
   }
 }
 
-template <int NKD, bool BACKWARD>
-cudaError_t launch_one(const pls_ctx* ctx, const GenGemmParams& p, int64_t grid, cudaStream_t stream) {
-  const size_t smem = gen_gemm_smem_bytes(p.sp);
+template <int NKD, bool BACKWARD, bool RBF, int RT>
+cudaError_t launch_one(const pls_ctx* ctx, const GenGemmParams& p, cudaStream_t stream) {
+  using T = Tile<RT>;
+  int64_t grid = ((p.n_rows + T::BR - 1) / T::BR) * ((p.j + T::BJ - 1) / T::BJ);
+  if (BACKWARD) grid *= p.splits;
+  if (grid <= 0) return cudaSuccess;
+  if (grid > 2147483647LL) return cudaErrorInvalidConfiguration;
+  const size_t smem = gen_gemm_smem_bytes<RT>(p.sp);
   if ((int64_t)smem > ctx->max_smem_optin) return cudaErrorInvalidConfiguration;
-  cudaError_t e = cudaFuncSetAttribute(gen_gemm_kernel<NKD, BACKWARD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(gen_gemm_kernel<NKD, BACKWARD, RBF, RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  gen_gemm_kernel<NKD, BACKWARD><<<(unsigned)grid, NTHREADS, smem, stream>>>(p);
+  gen_gemm_kernel<NKD, BACKWARD, RBF, RT><<<(unsigned)grid, NTHREADS, smem, stream>>>(p);
   return cudaGetLastError();
+}
+
+template <int NKD, bool BACKWARD>
+cudaError_t launch_kind(const pls_ctx* ctx, const GenGemmParams& p, cudaStream_t stream) {
+  const bool rbf = (p.kernel_id == PLS_KERNEL_RBF);
+  if (p.rt == 1) return rbf ? launch_one<NKD, BACKWARD, true, 1>(ctx, p, stream) : launch_one<NKD, BACKWARD, false, 1>(ctx, p, stream);
+  return rbf ? launch_one<NKD, BACKWARD, true, 2>(ctx, p, stream) : launch_one<NKD, BACKWARD, false, 2>(ctx, p, stream);
 }
 
 }  // namespace

@@ -11,9 +11,8 @@ namespace pls {
 #define PLS_CAT2(a, b) a##b
 #define PLS_CAT(a, b) PLS_CAT2(a, b)
 
-cudaError_t PLS_CAT(launch_gen_gemm_nkd, PLS_NKD)(bool backward, const pls_ctx* ctx, const GenGemmParams& p, int64_t grid,
-                                                   cudaStream_t stream) {
-  return backward ? launch_one<PLS_NKD, true>(ctx, p, grid, stream) : launch_one<PLS_NKD, false>(ctx, p, grid, stream);
+cudaError_t PLS_CAT(launch_gen_gemm_nkd, PLS_NKD)(bool backward, const pls_ctx* ctx, const GenGemmParams& p, cudaStream_t stream) {
+  return backward ? launch_kind<PLS_NKD, true>(ctx, p, stream) : launch_kind<PLS_NKD, false>(ctx, p, stream);
 }
 
 }  // namespace pls

@@ -11,6 +11,7 @@ struct pls_ctx {
   int device = 0;
   int sm_count = 0;
   int max_smem_optin = 0;
+  int tile_rt = 0;  // 0 = choose per launch from the particle count; 1 / 2 force a tile shape (PLS_B200_TILE_RT, tests)
   std::string error;
 };
 
@@ -31,11 +32,18 @@ struct GenGemmParams {
   int epilogue;  // PLS_EPI_* for the forward role; ignored by the backward role
   int splits;    // backward role: number of reduction splits (gridDim = tiles * splits)
   int accumulate;
+  int rt;  // tile shape: row tiles per warp (1: 64 x 256 CTA tile, 2: 128 x 128)
   double* out;
   int64_t ldo;
   const double* y;
   pls_cost cost;
 };
+
+// tile shape for a launch over j particle columns: wide tiles unless the slice is narrow
+inline int choose_tile_rt(const pls_ctx* ctx, int64_t j) {
+  if (ctx && (ctx->tile_rt == 1 || ctx->tile_rt == 2)) return ctx->tile_rt;
+  return (j <= 128) ? 2 : 1;
+}
 
 cudaError_t launch_gen_gemm_forward(const pls_ctx* ctx, const GenGemmParams& p, cudaStream_t stream);
 cudaError_t launch_gen_gemm_backward(const pls_ctx* ctx, const GenGemmParams& p, cudaStream_t stream);

@@ -85,9 +85,10 @@ class LangevinEngine:
         return out[:, : self.j]
 
     def cost_partials(self, particles: torch.Tensor, cost: nat.PlsCost, y: torch.Tensor) -> torch.Tensor:
-        """per-128-row-tile column sums of c(y, F) -> (tiles, J) without materialising F."""
+        """per-row-tile column sums of c(y, F) -> (tiles, J) without materialising F."""
         self._weights(particles)
-        tiles = (self.n + nat.TILE_ROWS - 1) // nat.TILE_ROWS
+        tile_rows = ops.forward_tile_rows(self.ctx, self.j)
+        tiles = (self.n + tile_rows - 1) // tile_rows
         part = torch.empty((max(tiles, 1), self.ldj), dtype=torch.float64, device=self.xa.device)
         ops.forward(self.ctx, self.kernel_id, self.xa, self.za, self.d, self.w, self.j, nat.EPI_COST, part, cost=cost, y=y)
         return part

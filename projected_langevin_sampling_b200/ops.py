@@ -99,6 +99,11 @@ def backward(ctx: nat.Context, kernel_id: int, za: torch.Tensor, xa: torch.Tenso
     return gp
 
 
+def forward_tile_rows(ctx: nat.Context, j: int) -> int:
+    """Rows per forward tile for a launch over j particle columns (granularity of the PLS_EPI_COST partial sums)."""
+    return int(ctx.lib.pls_forward_tile_rows(ctx.handle, j))
+
+
 def backward_splits(ctx: nat.Context, n_rows: int, m: int, j: int) -> int:
     return int(ctx.lib.pls_backward_splits(ctx.handle, n_rows, m, j))
 
@@ -134,7 +139,7 @@ def cost_derivative(ctx: nat.Context, cost: nat.PlsCost, y: torch.Tensor, f: tor
 
 def cost_value(ctx: nat.Context, cost: nat.PlsCost, y: torch.Tensor, f: torch.Tensor) -> torch.Tensor:
     n, j = f.shape
-    tiles = (n + nat.TILE_ROWS - 1) // nat.TILE_ROWS
+    tiles = (n + nat.COST_VALUE_TILE_ROWS - 1) // nat.COST_VALUE_TILE_ROWS
     partial = torch.empty((max(tiles, 1), j), dtype=F64, device=f.device)
     out = torch.empty((j,), dtype=F64, device=f.device)
     ctx.check(ctx.lib.pls_cost_value_f64(ctx.handle, C.byref(cost), y.data_ptr(), f.data_ptr(), _ld(f), n, j,
