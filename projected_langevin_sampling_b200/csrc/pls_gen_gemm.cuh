@@ -36,11 +36,6 @@ namespace {
 constexpr int SMEM_HEADER = 128 + 64 * 8;  // mbarriers + exp table
 constexpr int NWARPS = NTHREADS / 32;
 
-// The cost functors are called (not inlined) from the tile epilogue: 64 calls per thread per tile is noise next to the
-// main loop, and it keeps the kernel's code small.
-static __device__ __noinline__ double cost_derivative_call(const pls_cost& c, double y, double f) { return cost_derivative(c, y, f); }
-static __device__ __noinline__ double cost_value_call(const pls_cost& c, double y, double f) { return cost_value(c, y, f); }
-
 template <int RT>
 struct Tile {
   static constexpr int NT = 32 / RT;          // n8 column tiles per warp
@@ -52,7 +47,10 @@ struct Tile {
 
 template <int RT>
 __host__ __device__ inline size_t gen_gemm_smem_bytes(int sp) {
-  return SMEM_HEADER + sizeof(double) * (size_t)(STAGES * BK * Tile<RT>::SB + STAGES * BK * sp);
+  // pipeline buffers; the forward epilogue re-uses them to stage the BR x BJ output tile
+  const size_t pipeline = (size_t)(STAGES * BK * Tile<RT>::SB + STAGES * BK * sp);
+  const size_t staging = (size_t)(Tile<RT>::BR * Tile<RT>::SB);
+  return SMEM_HEADER + sizeof(double) * (pipeline > staging ? pipeline : staging);
 }
 
 template <int NKD, bool BACKWARD, bool RBF, int RT>
@@ -288,69 +286,51 @@ __global__ void __launch_bounds__(NTHREADS, 1) gen_gemm_kernel(const GenGemmPara
     return;
   }
 
-  if (p.epilogue == PLS_EPI_COST) {
-    // per-column sum over this tile's rows of c(y_n, F[n][j]) -> out[rt][j]
-    double ysel[RT];
-    bool rvalid[RT];
+  // Forward role: stage the F tile in shared memory (the pipeline buffers are idle: every issued copy has landed and been
+  // consumed), then one coalesced pass applies the cost functor -- inlined once, in a rolled loop with independent
+  // evaluations in flight -- and writes whole 128-byte lines.
+  __syncthreads();
+  double* sF = sB;  // [BR][SB]
 #pragma unroll
-    for (int h = 0; h < RT; ++h) {
-      const int64_t r = row0 + (warp * RT + h) * 8 + g;
-      rvalid[h] = r < p.n_rows;
-      ysel[h] = rvalid[h] ? p.y[r] : 0.0;
-    }
-    __syncthreads();  // every warp is done with the staging buffers; reuse stage 0 as reduction scratch
-    double* sred = sB;  // [8 warps][BJ]
+  for (int h = 0; h < RT; ++h) {
+    double* frow = sF + ((warp * RT + h) * 8 + g) * SB + 4 * t;
 #pragma unroll
     for (int pr = 0; pr < NPR; ++pr) {
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int nt = 2 * pr + (e & 1);
-        const int ce = e >> 1;
-        double v = 0.0;
-#pragma unroll
-        for (int h = 0; h < RT; ++h)
-          if (rvalid[h]) v += cost_value_call(p.cost, ysel[h], acc[h][nt][ce]);
-        v += __shfl_xor_sync(0xffffffffu, v, 4);
-        v += __shfl_xor_sync(0xffffffffu, v, 8);
-        v += __shfl_xor_sync(0xffffffffu, v, 16);
-        if (g == 0) sred[warp * BJ + 16 * pr + 4 * t + e] = v;
-      }
+      double2* dst = reinterpret_cast<double2*>(frow + 16 * pr);
+      dst[0] = make_double2(acc[h][2 * pr][0], acc[h][2 * pr + 1][0]);
+      dst[1] = make_double2(acc[h][2 * pr][1], acc[h][2 * pr + 1][1]);
     }
-    __syncthreads();
-    if (tid < BJ && j0 + tid < p.j) {
+  }
+  __syncthreads();
+  const int64_t rows_here = (p.n_rows - row0 < BR) ? (p.n_rows - row0) : BR;
+  const int64_t cols_here = (p.j - j0 < BJ) ? (p.j - j0) : BJ;
+
+  if (p.epilogue == PLS_EPI_COST) {
+    // per-column sum over this tile's rows (increasing row order) of c(y_n, F[n][j]) -> out[rt][j]
+    if (tid < cols_here) {
       double v = 0.0;
-#pragma unroll
-      for (int w = 0; w < NWARPS; ++w) v += sred[w * BJ + tid];
+      for (int r = 0; r < (int)rows_here; ++r) v += cost_value(p.cost, p.y[row0 + r], sF[r * SB + tid]);
       p.out[rt * p.ldo + j0 + tid] = v;
     }
     return;
   }
 
   const bool dcost = (p.epilogue == PLS_EPI_COST_DERIVATIVE);
-#pragma unroll
-  for (int h = 0; h < RT; ++h) {
-    const int64_t r = row0 + (warp * RT + h) * 8 + g;
-    if (r >= p.n_rows) continue;
-    const double yv = dcost ? p.y[r] : 0.0;
-    double* orow = p.out + r * p.ldo;
-#pragma unroll
-    for (int pr = 0; pr < NPR; ++pr) {
-      const int64_t col = j0 + 16 * pr + 4 * t;
-      double v[4] = {acc[h][2 * pr][0], acc[h][2 * pr + 1][0], acc[h][2 * pr][1], acc[h][2 * pr + 1][1]};
-      if (dcost) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) v[e] = cost_derivative_call(p.cost, yv, v[e]);
-      }
-      if (col + 3 < p.j) {
-        double2* dst = reinterpret_cast<double2*>(orow + col);
-        dst[0] = make_double2(v[0], v[1]);
-        dst[1] = make_double2(v[2], v[3]);
-      } else {
-#pragma unroll
-        for (int e = 0; e < 4; ++e)
-          if (col + e < p.j) orow[col + e] = v[e];
-      }
+  constexpr int PAIRS = BJ / 2;  // double2 per row
+#pragma unroll 2
+  for (int idx = tid; idx < BR * PAIRS; idx += NTHREADS) {
+    const int r = idx / PAIRS;
+    const int col = 2 * (idx - r * PAIRS);
+    if (r >= rows_here || col >= cols_here) continue;
+    double2 v = *reinterpret_cast<const double2*>(sF + r * SB + col);
+    if (dcost) {
+      const double yv = p.y[row0 + r];
+      v.x = cost_derivative(p.cost, yv, v.x);
+      v.y = cost_derivative(p.cost, yv, v.y);
     }
+    double* dst = p.out + (row0 + r) * p.ldo + j0 + col;
+    if (col + 1 < cols_here) *reinterpret_cast<double2*>(dst) = v;
+    else dst[0] = v.x;
   }
 }
 
