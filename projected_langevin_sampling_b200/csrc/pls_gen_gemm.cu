@@ -1,8 +1,54 @@
 // Dispatch of the generated-operand GEMM (kernel in pls_gen_gemm.cuh, instantiated per NKD in pls_gen_gemm_inst.cu).
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
 #include "pls_common.cuh"
 #include "pls_internal.h"
 
 namespace pls {
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point lookup (no link-time dependency on libcuda)
+static PFN_cuTensorMapEncodeTiled_v12000 encode_tiled() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = [] {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      sym = nullptr;
+    return reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(sym);
+  }();
+  return fn;
+}
+
+cudaError_t make_stream_maps(const pls_ctx*, const double* b, int64_t rows, int64_t ldb, int blocks, CUtensorMap* tm3,
+                             CUtensorMap* tm2, int* tma3d_ok) {
+  auto encode = encode_tiled();
+  if (!encode) return cudaErrorNotSupported;
+  if (rows <= 0 || ldb < 2 || (ldb & 1) || rows > 0x7fffffffLL || ldb > 0x7fffffffLL) return cudaErrorInvalidValue;
+  const cuuint32_t ones[3] = {1, 1, 1};
+  {  // [rows][ldb], box 32 rows x 16 columns
+    const cuuint64_t dims[2] = {(cuuint64_t)ldb, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ldb * 8};
+    const cuuint32_t box[2] = {16, (cuuint32_t)BK};
+    if (encode(tm2, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(b), dims, strides, box, ones,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return cudaErrorInvalidValue;
+  }
+  *tma3d_ok = 0;
+  const int64_t full_blocks = ldb / 16;
+  if (full_blocks > 0) {  // [ldb/16 column blocks][rows][16]: dimension 2 strides by 128 bytes INSIDE a row
+    const cuuint64_t dims[3] = {16, (cuuint64_t)rows, (cuuint64_t)full_blocks};
+    const cuuint64_t strides[2] = {(cuuint64_t)ldb * 8, 128};
+    const cuuint32_t box[3] = {16, (cuuint32_t)BK, (cuuint32_t)blocks};
+    if (encode(tm3, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double*>(b), dims, strides, box, ones,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
+      *tma3d_ok = 1;
+  }
+  if (!*tma3d_ok) *tm3 = *tm2;
+  return cudaSuccess;
+}
 
 #define PLS_DECL(k) \
   cudaError_t launch_gen_gemm_nkd##k(bool backward, const pls_ctx* ctx, const GenGemmParams& p, cudaStream_t stream);

@@ -3,7 +3,7 @@
 //     C[r][j] (+)= sum_k  kappa(row_r, red_k) * B[k][j]
 //
 //   forward role   rows = training points x_n, reduction = inducing points z_m, B = W = V~ P  (M x J)
-//                  -> F = k(X,Z) W, then the cost epilogue in registers            (orthonormal.py:98-108 + costs/*.py)
+//                  -> F = k(X,Z) W, then the cost epilogue                           (orthonormal.py:98-108 + costs/*.py)
 //   backward role  rows = inducing points z_m, reduction = training points x_n, B = d_2 c  (N x J), split over n
 //                  -> G'[m][j] = sum_n k(z_m, x_n) Dc[n][j]                        (orthonormal.py:151-155)
 //
@@ -20,12 +20,17 @@
 //   * the exponent tile itself is a DMMA: S = c_row + c_point + x~ . z~ (= -|x~ - z~|^2/2 + log sigma^2) comes out in
 //     C-fragment layout; the thread that holds S[g][2t], S[g][2t+1] uses exp of them as the A fragments of two k4
 //     steps whose k index t maps to reduction points 2t and 2t+1 (the B rows are addressed accordingly): no shuffle.
-//   * B (W or Dc rows) and the reduction-point rows are staged by the TMA engine (cp.async.bulk -> UBLKCP) through a
-//     3-stage mbarrier pipeline; every warp's lane 0 issues a share, all 8 warps consume; rows are padded by 2 doubles
-//     so the LDS.128 B-fragment reads are bank-conflict free.
+//   * B (W or Dc rows) is staged by ONE tensor-map TMA instruction per 32-row stage (cp.async.bulk.tensor.3d ->
+//     UTMALDG): the matrix is described as [column block of 16][row][16 doubles] and lands in shared memory as
+//     BJ/16 blocks of 32 rows x 128 bytes with the 128-byte swizzle, which makes the LDS.128 B-fragment reads
+//     bank-conflict free without padding (lane (g,t) reads 16-byte chunk g ^ (row & 7) of row 2t [+1]).  The
+//     reduction-point rows follow with one plain bulk copy.  3-stage full-barrier pipeline; a stage is refilled by the
+//     LAST warp to release it (atomic counter), so no warp ever waits to issue a copy.
 //   * the loop over 8-point groups is flat and branch-free (kernel kind is a template parameter) so ptxas can interleave
 //     the exponent chain of the NEXT k4 step with the 32 DMMAs of the current one.
 #pragma once
+#include <cuda.h>
+
 #include "pls_cost.cuh"
 #include "pls_internal.h"
 
@@ -33,36 +38,57 @@ namespace pls {
 
 namespace {
 
-constexpr int SMEM_HEADER = 128 + 64 * 8;  // mbarriers + exp table
 constexpr int NWARPS = NTHREADS / 32;
+constexpr int BLOCK_BYTES = BK * 128;  // one 16-column block of a stage: 32 rows x 128 bytes
 
 template <int RT>
 struct Tile {
   static constexpr int NT = 32 / RT;          // n8 column tiles per warp
   static constexpr int BR = tile_rows(RT);    // rows per CTA
   static constexpr int BJ = tile_cols(RT);    // columns per CTA
-  static constexpr int SB = BJ + 2;           // smem row stride of the streamed tile
-  static constexpr int NPR = NT / 2;          // column pairs (one LDS.128 each)
+  static constexpr int NPR = NT / 2;          // 16-column blocks = column pairs (one LDS.128 each)
+  static constexpr int STAGE_BYTES = NPR * BLOCK_BYTES;
+  static constexpr int SF = BJ + 2;           // row stride (doubles) of the forward epilogue's staging tile
 };
 
+// shared memory: [0, 1024) barriers + counters + exp table | STAGES x stage (1024-aligned) | STAGES x BK x sp points
 template <int RT>
 __host__ __device__ inline size_t gen_gemm_smem_bytes(int sp) {
-  // pipeline buffers; the forward epilogue re-uses them to stage the BR x BJ output tile
-  const size_t pipeline = (size_t)(STAGES * BK * Tile<RT>::SB + STAGES * BK * sp);
-  const size_t staging = (size_t)(Tile<RT>::BR * Tile<RT>::SB);
-  return SMEM_HEADER + sizeof(double) * (pipeline > staging ? pipeline : staging);
+  const size_t pipeline = (size_t)STAGES * Tile<RT>::STAGE_BYTES + sizeof(double) * (size_t)(STAGES * BK * sp);
+  const size_t staging = sizeof(double) * (size_t)(Tile<RT>::BR * Tile<RT>::SF);
+  return 1024 /* alignment slack */ + 1024 + (pipeline > staging ? pipeline : staging);
+}
+
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+                   smem_u32(dst)),
+               "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                   smem_u32(dst)),
+               "l"(tm), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ unsigned atom_add_acq_rel_shared(unsigned* addr, unsigned v) {
+  unsigned old;
+  asm volatile("atom.acq_rel.cta.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(addr)), "r"(v) : "memory");
+  return old;
 }
 
 template <int NKD, bool BACKWARD, bool RBF, int RT>
-__global__ void __launch_bounds__(NTHREADS, 1) gen_gemm_kernel(const GenGemmParams p) {
+__global__ void __launch_bounds__(NTHREADS, 1)
+    gen_gemm_kernel(const GenGemmParams p, const __grid_constant__ CUtensorMap tm3, const __grid_constant__ CUtensorMap tm2) {
   using T = Tile<RT>;
-  constexpr int NT = T::NT, BR = T::BR, BJ = T::BJ, SB = T::SB, NPR = T::NPR;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
-  uint64_t* empty = full + STAGES;
-  double* sExp = reinterpret_cast<double*>(smem_raw + 128);        // 2^(j/64)
-  double* sB = reinterpret_cast<double*>(smem_raw + SMEM_HEADER);  // [STAGES][BK][SB]
-  double* sP = sB + STAGES * BK * SB;                              // [STAGES][BK][sp]
+  constexpr int NT = T::NT, BR = T::BR, BJ = T::BJ, NPR = T::NPR, STAGE_BYTES = T::STAGE_BYTES, SF = T::SF;
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);  // the swizzle needs 1024-byte stages
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);                      // [STAGES]
+  unsigned* released = reinterpret_cast<unsigned*>(smem_raw + 64);             // [STAGES] warps done with the stage
+  double* sExp = reinterpret_cast<double*>(smem_raw + 128);                    // 2^(j/64)
+  unsigned char* sB = smem_raw + 1024;                                         // [STAGES][NPR][BK rows][128 bytes], swizzled
+  double* sP = reinterpret_cast<double*>(sB + STAGES * STAGE_BYTES);           // [STAGES][BK][sp]
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -103,18 +129,41 @@ __global__ void __launch_bounds__(NTHREADS, 1) gen_gemm_kernel(const GenGemmPara
   const int total_groups = (red_len + 7) >> 3;  // BK is a multiple of 8: groups never straddle chunks
 
   // ---- one-time setup -------------------------------------------------------------------------------------------
-  // zero the staging buffers: rows never written by a copy (reduction tail) must hold finite values
-  for (int i = tid; i < STAGES * BK * SB + STAGES * BK * sp; i += NTHREADS) sB[i] = 0.0;
+  // point rows past the end of the reduction are never copied: keep them finite
+  for (int i = tid; i < STAGES * BK * sp; i += NTHREADS) sP[i] = 0.0;
   if (tid < 64) sExp[tid] = kExp2Table[tid];
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full[s], NWARPS);
-      mbar_init(&empty[s], NWARPS);
+      mbar_init(&full[s], 1);
+      released[s] = 0;
     }
     fence_mbar_init();
   }
   fence_proxy_async();  // generic-proxy zero fill ordered before the async-proxy bulk copies
   __syncthreads();
+
+  // One thread fills a stage: one tensor-map copy for the streamed tile (all BJ/16 column blocks; rows or columns outside
+  // the matrix arrive as zeros), one bulk copy for the reduction-point rows.  The 3-D map cannot describe a partial last
+  // column block, so a tile that contains one uses the 2-D map block by block.
+  const bool use3d = p.tma3d && (j0 + BJ <= p.full_blocks * 16 || p.full_blocks * 16 == p.ldb);
+  auto issue = [&](int c) {
+    const int stage = c % STAGES;
+    const int64_t k0 = begin + (int64_t)c * BK;
+    const int kc = (int)((end - k0 < BK) ? (end - k0) : BK);
+    uint64_t* bar = &full[stage];
+    mbar_expect_tx(bar, (uint32_t)(STAGE_BYTES + kc * sp * 8));
+    unsigned char* dst = sB + stage * STAGE_BYTES;
+    if (use3d) {
+      tma_load_3d(dst, &tm3, 0, (int)k0, (int)(j0 >> 4), bar);
+    } else {
+#pragma unroll 1
+      for (int blk = 0; blk < NPR; ++blk) tma_load_2d(dst + blk * BLOCK_BYTES, &tm2, (int)j0 + 16 * blk, (int)k0, bar);
+    }
+    bulk_g2s(sP + stage * BK * sp, p.red_aug + k0 * sp, (uint32_t)(kc * sp * 8), bar);
+  };
+  if (tid == 0) {
+    for (int c = 0; c < STAGES && c < nchunks; ++c) issue(c);
+  }
 
   // row-side exponent fragments (A operand of the S DMMA): row g of each of this warp's RT row tiles.  Coordinates only;
   // the c entry (column d of the augmented row) seeds the accumulator together with the point's c.
@@ -132,25 +181,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) gen_gemm_kernel(const GenGemmPara
     crow[h] = rv ? p.rows_aug[r * sp + p.d] : 0.0;
   }
 
-  const int64_t cw = (p.ldb - j0 < BJ) ? (p.ldb - j0) : BJ;  // columns copied per row (ldb even => 16-byte multiple)
-  // Every warp's lane 0 issues its share of a stage (rows warp, warp + 8, ... of the streamed tile; warp 0 adds the point
-  // rows) and posts the bytes it issued on the stage's full barrier (8 arrivals), so no single warp carries the copy
-  // issue cost on its critical path.
-  auto issue = [&](int c) {
-    const int stage = c % STAGES;
-    const int64_t k0 = begin + (int64_t)c * BK;
-    const int kc = (int)((end - k0 < BK) ? (end - k0) : BK);
-    uint64_t* bar = &full[stage];
-    const int my_rows = (kc > warp) ? ((kc - warp + NWARPS - 1) / NWARPS) : 0;
-    uint32_t bytes = (uint32_t)(my_rows * cw * 8);
-    if (warp == 0) bytes += (uint32_t)(kc * sp * 8);
-    mbar_expect_tx(bar, bytes);
-    double* dst = sB + stage * BK * SB;
-    const double* src = p.b + k0 * p.ldb + j0;
-    for (int r = warp; r < kc; r += NWARPS) bulk_g2s(dst + r * SB, src + (int64_t)r * p.ldb, (uint32_t)(cw * 8), bar);
-    if (warp == 0) bulk_g2s(sP + stage * BK * sp, p.red_aug + k0 * sp, (uint32_t)(kc * sp * 8), bar);
-  };
-
   double acc[RT][NT][2];
 #pragma unroll
   for (int h = 0; h < RT; ++h)
@@ -159,10 +189,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) gen_gemm_kernel(const GenGemmPara
       acc[h][nt][0] = 0.0;
       acc[h][nt][1] = 0.0;
     }
-
-  if (lane == 0) {
-    for (int c = 0; c < STAGES - 1 && c < nchunks; ++c) issue(c);
-  }
 
   // ---- main loop over groups of 8 reduction points ------------------------------------------------------------------
   // Software-pipelined at k4-step granularity: while the DMMAs of one k4 step (one reduction point per thread) are
@@ -189,10 +215,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) gen_gemm_kernel(const GenGemmPara
     const double v = RBF ? gram_exp_fast(sv, sExp) : sv;
     return valid ? v : 0.0;
   };
-  auto mma_step = [&](const double* brow, const double (&ka)[RT]) {
+  // one k4 step: brow = this lane's 16-byte chunk of its reduction row in column block 0
+  auto mma_step = [&](const unsigned char* brow, const double (&ka)[RT]) {
 #pragma unroll
     for (int pr = 0; pr < NPR; ++pr) {
-      const double2 bv = *reinterpret_cast<const double2*>(brow + 16 * pr);
+      const double2 bv = *reinterpret_cast<const double2*>(brow + pr * BLOCK_BYTES);
 #pragma unroll
       for (int h = 0; h < RT; ++h) {
         dmma(acc[h][2 * pr][0], acc[h][2 * pr][1], ka[h], bv.x);
@@ -200,6 +227,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) gen_gemm_kernel(const GenGemmPara
       }
     }
   };
+  // swizzled position of columns (2g, 2g+1) of rows 2t and 2t+1 within an 8-row group of a column block
+  const int off0 = (2 * t) * 128 + ((g ^ (2 * t)) << 4);
+  const int off1 = (2 * t + 1) * 128 + ((g ^ (2 * t + 1)) << 4);
 
   double s[RT][2];  // exponents of the group in flight
   double k0[RT];    // Gram values of k4 step 0 (point 2t)
@@ -222,31 +252,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) gen_gemm_kernel(const GenGemmPara
     const int nstage = cn % STAGES;
     if (cn != c) mbar_wait(&full[nstage], ((uint32_t)(cn / STAGES)) & 1u);
 
-    const int p0 = grp * 8 + 2 * t;  // this thread's two reduction points: p0 (k4 step 0) and p0 + 1 (k4 step 1)
-    const int pg = gi * 8 + 2 * t;   // ... counted from `begin`
-    const double* b0 = sB + (stage * BK + p0) * SB + 2 * g;
+    const int pg = gi * 8 + 2 * t;  // this thread's two reduction points (k4 steps 0 and 1), counted from `begin`
+    const unsigned char* bgrp = sB + stage * STAGE_BYTES + grp * 1024;
     // k4 step 0 with k0; meanwhile the Gram values of step 1
     double k1[RT];
 #pragma unroll
     for (int h = 0; h < RT; ++h) k1[h] = gram_value(s[h][1], pg + 1 < red_len);
-    mma_step(b0, k0);
+    mma_step(bgrp + off0, k0);
     // k4 step 1 with k1; meanwhile exponents + step-0 Gram values of the next group
     exponent_tile(sP + nstage * BK * sp, gn & 3, s);
     const bool nvalid = (gn != gi) && (gn * 8 + 2 * t < red_len);
 #pragma unroll
     for (int h = 0; h < RT; ++h) k0[h] = gram_value(s[h][0], nvalid);
-    mma_step(b0 + SB, k1);
+    mma_step(bgrp + off1, k1);
 
-    if (grp == 3 || gi + 1 == total_groups) {  // chunk c fully consumed by this warp
+    if (grp == 3 && c + STAGES < nchunks) {  // chunk c fully consumed by this warp and its stage is needed again
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(&empty[stage]);
-        // refill the stage consumed in chunk c-1 with chunk c + STAGES - 1: every warp has long left that stage, so the
-        // wait does not stall, and the copies have one full chunk of compute to land
-        const int cf = c + STAGES - 1;
-        if (cf < nchunks) {
-          mbar_wait(&empty[cf % STAGES], (((uint32_t)(cf / STAGES)) & 1u) ^ 1u);
-          issue(cf);
+        // the last warp to release the stage refills it: nobody waits
+        if (atom_add_acq_rel_shared(&released[stage], 1u) == NWARPS - 1) {
+          released[stage] = 0;
+          issue(c + STAGES);
         }
       }
     }
@@ -290,10 +316,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) gen_gemm_kernel(const GenGemmPara
   // consumed), then one coalesced pass applies the cost functor -- inlined once, in a rolled loop with independent
   // evaluations in flight -- and writes whole 128-byte lines.
   __syncthreads();
-  double* sF = sB;  // [BR][SB]
+  double* sF = reinterpret_cast<double*>(sB);  // [BR][SF]
 #pragma unroll
   for (int h = 0; h < RT; ++h) {
-    double* frow = sF + ((warp * RT + h) * 8 + g) * SB + 4 * t;
+    double* frow = sF + ((warp * RT + h) * 8 + g) * SF + 4 * t;
 #pragma unroll
     for (int pr = 0; pr < NPR; ++pr) {
       double2* dst = reinterpret_cast<double2*>(frow + 16 * pr);
@@ -309,7 +335,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gen_gemm_kernel(const GenGemmPara
     // per-column sum over this tile's rows (increasing row order) of c(y_n, F[n][j]) -> out[rt][j]
     if (tid < cols_here) {
       double v = 0.0;
-      for (int r = 0; r < (int)rows_here; ++r) v += cost_value(p.cost, p.y[row0 + r], sF[r * SB + tid]);
+      for (int r = 0; r < (int)rows_here; ++r) v += cost_value(p.cost, p.y[row0 + r], sF[r * SF + tid]);
       p.out[rt * p.ldo + j0 + tid] = v;
     }
     return;
@@ -322,7 +348,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gen_gemm_kernel(const GenGemmPara
     const int r = idx / PAIRS;
     const int col = 2 * (idx - r * PAIRS);
     if (r >= rows_here || col >= cols_here) continue;
-    double2 v = *reinterpret_cast<const double2*>(sF + r * SB + col);
+    double2 v = *reinterpret_cast<const double2*>(sF + r * SF + col);
     if (dcost) {
       const double yv = p.y[row0 + r];
       v.x = cost_derivative(p.cost, yv, v.x);
@@ -335,17 +361,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) gen_gemm_kernel(const GenGemmPara
 }
 
 template <int NKD, bool BACKWARD, bool RBF, int RT>
-cudaError_t launch_one(const pls_ctx* ctx, const GenGemmParams& p, cudaStream_t stream) {
+cudaError_t launch_one(const pls_ctx* ctx, GenGemmParams p, cudaStream_t stream) {
   using T = Tile<RT>;
   int64_t grid = ((p.n_rows + T::BR - 1) / T::BR) * ((p.j + T::BJ - 1) / T::BJ);
   if (BACKWARD) grid *= p.splits;
-  if (grid <= 0) return cudaSuccess;
+  if (grid <= 0 || p.red_total <= 0) return cudaSuccess;
   if (grid > 2147483647LL) return cudaErrorInvalidConfiguration;
   const size_t smem = gen_gemm_smem_bytes<RT>(p.sp);
   if ((int64_t)smem > ctx->max_smem_optin) return cudaErrorInvalidConfiguration;
-  cudaError_t e = cudaFuncSetAttribute(gen_gemm_kernel<NKD, BACKWARD, RBF, RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  CUtensorMap tm3, tm2;
+  cudaError_t e = make_stream_maps(ctx, p.b, p.red_total, p.ldb, T::NPR, &tm3, &tm2, &p.tma3d);
   if (e != cudaSuccess) return e;
-  gen_gemm_kernel<NKD, BACKWARD, RBF, RT><<<(unsigned)grid, NTHREADS, smem, stream>>>(p);
+  p.full_blocks = p.ldb / 16;
+  e = cudaFuncSetAttribute(gen_gemm_kernel<NKD, BACKWARD, RBF, RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  gen_gemm_kernel<NKD, BACKWARD, RBF, RT><<<(unsigned)grid, NTHREADS, smem, stream>>>(p, tm3, tm2);
   return cudaGetLastError();
 }
 

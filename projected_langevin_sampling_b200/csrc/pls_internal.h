@@ -7,6 +7,8 @@
 
 #include "../../include/pls_b200.h"
 
+struct CUtensorMap_st;  // <cuda.h>
+
 struct pls_ctx {
   int device = 0;
   int sm_count = 0;
@@ -33,6 +35,8 @@ struct GenGemmParams {
   int splits;    // backward role: number of reduction splits (gridDim = tiles * splits)
   int accumulate;
   int rt;  // tile shape: row tiles per warp (1: 64 x 256 CTA tile, 2: 128 x 128)
+  int tma3d;            // set by the launcher: the 3-D tensor map of the streamed matrix is usable
+  int64_t full_blocks;  // set by the launcher: complete 16-column blocks per row of the streamed matrix (ldb / 16)
   double* out;
   int64_t ldo;
   const double* y;
@@ -44,6 +48,12 @@ inline int choose_tile_rt(const pls_ctx* ctx, int64_t j) {
   if (ctx && (ctx->tile_rt == 1 || ctx->tile_rt == 2)) return ctx->tile_rt;
   return (j <= 128) ? 2 : 1;
 }
+
+// Tensor maps of the streamed matrix b (rows x ldb doubles, 16-byte aligned, ldb even) for the hot kernel's stages of 32 rows
+// x (16 * blocks) columns, 128-byte swizzle: tm3 = [ldb/16 column blocks][rows][16] (one copy per stage), tm2 = [rows][ldb]
+// with a 32 x 16 box (one copy per column block; handles a partial last block).  *tma3d_ok = 0 if the driver rejects tm3.
+cudaError_t make_stream_maps(const pls_ctx* ctx, const double* b, int64_t rows, int64_t ldb, int blocks, ::CUtensorMap_st* tm3,
+                             ::CUtensorMap_st* tm2, int* tma3d_ok);
 
 cudaError_t launch_gen_gemm_forward(const pls_ctx* ctx, const GenGemmParams& p, cudaStream_t stream);
 cudaError_t launch_gen_gemm_backward(const pls_ctx* ctx, const GenGemmParams& p, cudaStream_t stream);
