@@ -126,7 +126,6 @@ __global__ void __launch_bounds__(NTHREADS, 1)
   }
   const int red_len = (int)(end - begin);
   const int nchunks = (red_len + BK - 1) / BK;
-  const int total_groups = (red_len + 7) >> 3;  // BK is a multiple of 8: groups never straddle chunks
 
   // ---- one-time setup -------------------------------------------------------------------------------------------
   // point rows past the end of the reduction are never copied: keep them finite
@@ -241,32 +240,36 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 #pragma unroll
     for (int h = 0; h < RT; ++h) k0[h] = gram_value(s[h][0], 2 * t < red_len);
   }
+  int stage = 0;
+  uint32_t phase = 0;  // of the chunk being consumed
 #pragma unroll 1
-  for (int gi = 0; gi < total_groups; ++gi) {
-    const int c = gi >> 2;  // BK / 8 = 4 groups per chunk
-    const int grp = gi & 3;
-    const int stage = c % STAGES;
-    // the group after this one: the next chunk's stage must have landed before its exponents are formed
-    const int gn = (gi + 1 < total_groups) ? gi + 1 : gi;
-    const int cn = gn >> 2;
-    const int nstage = cn % STAGES;
-    if (cn != c) mbar_wait(&full[nstage], ((uint32_t)(cn / STAGES)) & 1u);
-
-    const int pg = gi * 8 + 2 * t;  // this thread's two reduction points (k4 steps 0 and 1), counted from `begin`
-    const unsigned char* bgrp = sB + stage * STAGE_BYTES + grp * 1024;
-    // k4 step 0 with k0; meanwhile the Gram values of step 1
-    double k1[RT];
+  for (int c = 0; c < nchunks; ++c) {
+    // One iteration = one 32-point stage = 4 groups, fully unrolled into a single basic block (264 DMMAs).  The next stage
+    // must have landed before the last group forms the exponents of the next chunk's first group; it was issued two chunk
+    // times ago, so waiting for it here, once per chunk, costs nothing.
+    const int nstage = (stage + 1 == STAGES) ? 0 : stage + 1;
+    const uint32_t nphase = (nstage == 0) ? (phase ^ 1u) : phase;
+    if (c + 1 < nchunks) mbar_wait(&full[nstage], nphase);
+    const unsigned char* bchunk = sB + stage * STAGE_BYTES;
+    const double* Pt = sP + stage * BK * sp;
+    const double* Pn = sP + nstage * BK * sp;
+    const int base = c * BK + 2 * t;  // this thread's first reduction point of the chunk, counted from `begin`
 #pragma unroll
-    for (int h = 0; h < RT; ++h) k1[h] = gram_value(s[h][1], pg + 1 < red_len);
-    mma_step(bgrp + off0, k0);
-    // k4 step 1 with k1; meanwhile exponents + step-0 Gram values of the next group
-    exponent_tile(sP + nstage * BK * sp, gn & 3, s);
-    const bool nvalid = (gn != gi) && (gn * 8 + 2 * t < red_len);
+    for (int grp = 0; grp < BK / 8; ++grp) {
+      const int pg = base + 8 * grp;  // this thread's two reduction points: pg (k4 step 0) and pg + 1 (k4 step 1)
+      // k4 step 0 with k0; meanwhile the Gram values of step 1
+      double k1[RT];
 #pragma unroll
-    for (int h = 0; h < RT; ++h) k0[h] = gram_value(s[h][0], nvalid);
-    mma_step(bgrp + off1, k1);
-
-    if (grp == 3 && c + STAGES < nchunks) {  // chunk c fully consumed by this warp and its stage is needed again
+      for (int h = 0; h < RT; ++h) k1[h] = gram_value(s[h][1], pg + 1 < red_len);
+      mma_step(bchunk + grp * 1024 + off0, k0);
+      // k4 step 1 with k1; meanwhile exponents + step-0 Gram values of the next group (past the end: masked)
+      if (grp + 1 < BK / 8) exponent_tile(Pt, grp + 1, s);
+      else exponent_tile(Pn, 0, s);
+#pragma unroll
+      for (int h = 0; h < RT; ++h) k0[h] = gram_value(s[h][0], pg + 8 < red_len);
+      mma_step(bchunk + grp * 1024 + off1, k1);
+    }
+    if (c + STAGES < nchunks) {  // chunk c fully consumed by this warp and its stage is needed again
       __syncwarp();
       if (lane == 0) {
         // the last warp to release the stage refills it: nobody waits
@@ -276,6 +279,8 @@ __global__ void __launch_bounds__(NTHREADS, 1)
         }
       }
     }
+    stage = nstage;
+    phase = nphase;
   }
 
   // ---- epilogue ---------------------------------------------------------------------------------------------------

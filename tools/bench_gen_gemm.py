@@ -25,9 +25,11 @@ def main():
     ap.add_argument("--rt", type=int, default=0)
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--splits", type=int, default=0)
+    ap.add_argument("--kernel", type=str, default="rbf", choices=["rbf", "linear"])
     ap.add_argument("--roles", type=str, default="forward,backward")
     args = ap.parse_args()
 
+    kid = nat.KERNEL_RBF if args.kernel == "rbf" else nat.KERNEL_LINEAR
     ctx = nat.context()
     ctx.lib.pls_set_tile_shape(ctx.handle, args.rt)
     g = torch.Generator().manual_seed(0)
@@ -36,8 +38,8 @@ def main():
     z = x[:m].clone()
     inv_ls = [1.0 / (d ** 0.5 * (0.75 + 0.5 * k / max(d - 1, 1))) for k in range(d)]
     centre = z.mean(0).tolist()
-    xa = ops.prepare_points(ctx, nat.KERNEL_RBF, x, inv_ls, centre, 0.0)
-    za = ops.prepare_points(ctx, nat.KERNEL_RBF, z, inv_ls, centre, 0.0)
+    xa = ops.prepare_points(ctx, kid, x, inv_ls, centre, 0.0)
+    za = ops.prepare_points(ctx, kid, z, inv_ls, centre, 0.0)
     w = (torch.randn(m, j, generator=g, dtype=torch.float64) / m).cuda()
     y = torch.randn(n, generator=g, dtype=torch.float64).cuda()
     cost = nat.PlsCost()
@@ -49,7 +51,7 @@ def main():
     splits = args.splits or ops.backward_splits(ctx, n, m, j)
     gp = torch.zeros(splits, m, j, dtype=torch.float64).cuda()
     flops = 2.0 * n * m * j
-    res = {"n": n, "m": m, "d": d, "j": j, "rt": args.rt, "epilogue": args.epilogue, "splits": splits}
+    res = {"n": n, "m": m, "d": d, "j": j, "rt": args.rt, "epilogue": args.epilogue, "kernel": args.kernel, "splits": splits}
 
     def timed(fn):
         fn()
@@ -65,10 +67,10 @@ def main():
         return best
 
     if "forward" in args.roles:
-        ms = timed(lambda: ops.forward(ctx, nat.KERNEL_RBF, xa, za, d, w, j, args.epilogue, out, cost=cost, y=y))
+        ms = timed(lambda: ops.forward(ctx, kid, xa, za, d, w, j, args.epilogue, out, cost=cost, y=y))
         res["forward_ms"], res["forward_tflops"] = round(ms, 3), round(flops / ms / 1e9, 3)
     if "backward" in args.roles:
-        ms = timed(lambda: ops.backward(ctx, nat.KERNEL_RBF, za, xa, d, dc, j, gp, splits, accumulate=False))
+        ms = timed(lambda: ops.backward(ctx, kid, za, xa, d, dc, j, gp, splits, accumulate=False))
         res["backward_ms"], res["backward_tflops"] = round(ms, 3), round(flops / ms / 1e9, 3)
     print(json.dumps(res))
 
