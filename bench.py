@@ -423,7 +423,9 @@ def main():
     peak = peak_file or peak_live
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get(args.workload)
+        traffic_rec = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get(args.workload)
+        if traffic_rec and not (args.n or args.j):
+            traffic = traffic_rec["per_launch_bytes_mean"]
     except Exception:
         pass
     n, m, j = workload["n"], workload["m"], workload["j"]
@@ -431,6 +433,8 @@ def main():
     roofline = {
         "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
         "traffic": traffic,
+        "traffic_note": "DRAM bytes per launch (mean of the forward and backward roles) from one ncu --set full capture of this command, "
+                        "profiles/roofline_traffic.json; the kernel is FP64-pipe bound, traffic ~= the Dc chunk written / read once",
         "kernel": "pls::gen_gemm_kernel (forward + backward roles; FP64 DMMA.8x8x4, no tcgen05 kind exists for f64)",
         "algorithmic_flops_per_step": 4.0 * n * m * j,
         "per_role": {k: ksum[k] for k in ("forward", "backward") if k in ksum},

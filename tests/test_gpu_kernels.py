@@ -106,3 +106,82 @@ def test_argument_errors_are_reported_not_thrown(ctx):
     assert rc != 0 and b"unknown kernel_id" in ctx.lib.pls_last_error(ctx.handle)
     with pytest.raises(nat.NativeLibraryError):
         ctx.check(rc)
+
+
+@pytest.mark.parametrize("rt", [1, 2])
+@pytest.mark.parametrize(
+    "n,m,d,j,ldw,lddc",
+    [
+        (130, 70, 26, 1, 2, 2),          # the largest supported D, a single particle
+        (64, 32, 4, 256, 256, 256),      # exactly one wide tile, one pipeline stage
+        (1000, 257, 7, 513, 530, 514),   # ragged everything; leading dimensions that are not multiples of 16 (2-D TMA path)
+        (333, 97, 1, 300, 304, 320),     # D = 1; leading dimensions that are multiples of 16 (3-D TMA path)
+        (40, 5, 3, 20, 32, 20),          # fewer reduction points than one 8-point group
+    ],
+)
+def test_generated_operand_gemm_tile_shapes(ctx, rt, n, m, d, j, ldw, lddc):
+    """Both CTA tile shapes (64 x 256 and 128 x 128), both TMA descriptor paths, ragged edges: forward, backward with
+    several split counts and the cost-sum epilogue against dense torch algebra on pls_gram_f64's matrix."""
+    from projected_langevin_sampling_b200 import _native as nat, ops
+
+    ctx.lib.pls_set_tile_shape(ctx.handle, rt)
+    try:
+        g = torch.Generator().manual_seed(1000 * n + j)
+        x = torch.randn(n, d, generator=g, dtype=torch.float64).cuda()
+        z = torch.randn(m, d, generator=g, dtype=torch.float64).cuda()
+        inv_ls = [1.0 / (1.0 + 0.1 * k + d ** 0.5) for k in range(d)]
+        centre = z.mean(0).tolist()
+        xa = ops.prepare_points(ctx, nat.KERNEL_RBF, x, inv_ls, centre, 0.0)
+        za = ops.prepare_points(ctx, nat.KERNEL_RBF, z, inv_ls, centre, float(np.log(0.8)))
+        k_xz = ops.gram(ctx, nat.KERNEL_RBF, xa, za, d)
+        w_store = torch.randn(m, ldw, generator=g, dtype=torch.float64).cuda()
+        f_store = torch.full((n, ldw), 3.0, dtype=torch.float64).cuda()
+        ops.forward(ctx, nat.KERNEL_RBF, xa, za, d, w_store, j, nat.EPI_PREDICTION, f_store)
+        want_f = k_xz @ w_store[:, :j]
+        scale = max(1.0, want_f.abs().max().item())
+        assert (f_store[:, :j] - want_f).abs().max().item() < 1e-12 * scale
+        assert (f_store[:, j:] == 3.0).all()
+        # cost-sum epilogue: per-row-tile partial sums of the Gaussian cost
+        y = torch.randn(n, generator=g, dtype=torch.float64).cuda()
+        cost = nat.PlsCost()
+        cost.cost_id, cost.link_id, cost.closed_form, cost.observation_noise = nat.COST_GAUSSIAN, nat.LINK_IDENTITY, 1, 0.3
+        tr = ops.forward_tile_rows(ctx, j)
+        assert tr == (64 if rt == 1 else 128)
+        tiles = (n + tr - 1) // tr
+        part = torch.zeros(tiles, ldw, dtype=torch.float64).cuda()
+        ops.forward(ctx, nat.KERNEL_RBF, xa, za, d, w_store, j, nat.EPI_COST, part, cost=cost, y=y)
+        want_c = ((want_f - y[:, None]) ** 2 / (2 * 0.3)).sum(0)
+        assert (part[:, :j].sum(0) - want_c).abs().max().item() < 1e-11 * max(1.0, want_c.abs().max().item())
+        dc_store = torch.randn(n, lddc, generator=g, dtype=torch.float64).cuda()
+        want_g = k_xz.T @ dc_store[:, :j]
+        for splits in (1, 2, 5):
+            gp = torch.full((splits, m, lddc), -2.0, dtype=torch.float64).cuda()
+            ops.backward(ctx, nat.KERNEL_RBF, za, xa, d, dc_store, j, gp, splits, accumulate=False)
+            out = torch.empty(m, lddc, dtype=torch.float64).cuda()
+            ops.reduce_splits(ctx, gp, j, out)
+            assert (out[:, :j] - want_g).abs().max().item() < 1e-11 * max(1.0, want_g.abs().max().item())
+            assert (gp[:, :, j:] == -2.0).all()
+    finally:
+        ctx.lib.pls_set_tile_shape(ctx.handle, 0)
+
+
+def test_non_finite_cost_derivative_stays_in_its_column(ctx):
+    """An Inf in Dc (Poisson at F = 0 produces one, costs/poisson.py:76-82 has no guard) must only affect its own particle
+    column, as in the reference's dense product -- also when it sits in a row past the end of another split."""
+    from projected_langevin_sampling_b200 import _native as nat, ops
+
+    g = torch.Generator().manual_seed(5)
+    n, m, d, j = 500, 40, 2, 64
+    x = torch.randn(n, d, generator=g, dtype=torch.float64).cuda()
+    z = x[:m].clone()
+    xa = ops.prepare_points(ctx, nat.KERNEL_RBF, x, [1.0, 1.0], [0.0, 0.0], 0.0)
+    za = ops.prepare_points(ctx, nat.KERNEL_RBF, z, [1.0, 1.0], [0.0, 0.0], 0.0)
+    dc = torch.randn(n, j, generator=g, dtype=torch.float64).cuda()
+    dc[321, 7] = float("inf")
+    splits = 3
+    gp = torch.zeros(splits, m, j, dtype=torch.float64).cuda()
+    ops.backward(ctx, nat.KERNEL_RBF, za, xa, d, dc, j, gp, splits, accumulate=False)
+    out = torch.empty(m, j, dtype=torch.float64).cuda()
+    ops.reduce_splits(ctx, gp, j, out)
+    finite_cols = torch.isfinite(out).all(0)
+    assert not finite_cols[7] and finite_cols[torch.arange(j).cuda() != 7].all()
