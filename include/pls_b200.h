@@ -48,7 +48,8 @@ enum { PLS_LINK_IDENTITY = 0, PLS_LINK_SIGMOID = 1, PLS_LINK_PROBIT = 2, PLS_LIN
 enum {
   PLS_EPI_PREDICTION = 0,      /* F = k(X,Z) W                      (n x J)        orthonormal.py:98-108            */
   PLS_EPI_COST_DERIVATIVE = 1, /* d_2 c(y, F)                       (n x J)        PLS.calculate_cost_derivative    */
-  PLS_EPI_COST = 2             /* per row tile: sum_n c(y_n,F)      (tiles x J)    PLS.calculate_cost               */
+  PLS_EPI_COST = 2,            /* per row tile: sum_n c(y_n,F)      (tiles x J)    PLS.calculate_cost               */
+  PLS_EPI_COST_DERIVATIVE_AND_COST = 3 /* both of the above in one pass (pls_forward_step_f64 only)                  */
 };
 /* Langevin noise source for pls_project_update_f64 */
 enum {
@@ -137,6 +138,15 @@ int pls_gemm_f64(pls_ctx* ctx, int trans_a, const double* a, int64_t lda, const 
 int pls_forward_f64(pls_ctx* ctx, int kernel_id, const double* xa, int64_t n, const double* za, int64_t m, int d,
                     const double* w, int64_t ldw, int64_t j, int epilogue, const pls_cost* cost, const double* y,
                     double* out, int64_t ldo, void* stream);
+
+/* pls_forward_f64 with the COST_DERIVATIVE epilogue that ALSO writes the per-row-tile cost sums of the COST epilogue
+ * (cost_partial: ceil(n / pls_forward_tile_rows(ctx, j)) x j, ldcp) from the same F tile: one forward per Langevin step
+ * serves both the gradient and the energy potential the training loop reads every step
+ * (experiments/trainers.py:153-158 runs PLS.calculate_particle_update AND PLS.calculate_energy_potential, i.e. two
+ * forwards, per epoch). */
+int pls_forward_step_f64(pls_ctx* ctx, int kernel_id, const double* xa, int64_t n, const double* za, int64_t m, int d,
+                         const double* w, int64_t ldw, int64_t j, const pls_cost* cost, const double* y, double* dc,
+                         int64_t lddc, double* cost_partial, int64_t ldcp, void* stream);
 
 /* Back-projection with on-the-fly Gram tiles, split `splits` ways over the training rows [0, n) of xa:
  *   gp[s][m][j] (+)= sum_{n in split s} k(z_m, x_n) dc[n][j]

@@ -456,6 +456,44 @@ class PLSOracle:
 
 
 # ----------------------------------------------------------------------------------------------------------------
+# the caller of the hot path -- experiments/early_stopper.py:4-24, experiments/trainers.py:139-162
+# ----------------------------------------------------------------------------------------------------------------
+class EarlyStopperOracle:
+    """experiments/early_stopper.py:4-24: stop on a non-finite loss, or once the loss has failed to improve on its minimum
+    for `patience` of accumulated SIMULATED time (sum of step sizes); an improvement resets the clock."""
+
+    def __init__(self, patience: float = 1e-4):
+        self.patience = patience
+        self.simulation_time = 0
+        self.min_loss = float("inf")
+
+    def should_stop(self, loss: float, step_size: float) -> bool:
+        if not np.isfinite(loss):
+            return True
+        if loss >= self.min_loss:
+            self.simulation_time += step_size
+            return self.simulation_time >= self.patience
+        self.min_loss = loss
+        self.simulation_time = 0
+        return False
+
+
+def train_pls_oracle(pls: "PLSOracle", particles: torch.Tensor, number_of_epochs: int, step_size: float,
+                     early_stopper_patience: float) -> Tuple[torch.Tensor, list]:
+    """experiments/trainers.py:139-162: per epoch P += update(P) (noise from torch's global CPU generator), E = energy(P);
+    the early stopper is asked BEFORE the energy is appended, so a stopping epoch's update is kept but its energy is not."""
+    energy_potentials = []
+    stopper = EarlyStopperOracle(patience=early_stopper_patience)
+    for _ in range(number_of_epochs):
+        particles = particles + pls.calculate_particle_update(particles, step_size)
+        energy = pls.calculate_energy_potential(particles)
+        if stopper.should_stop(loss=energy, step_size=step_size):
+            break
+        energy_potentials.append(energy)
+    return particles, energy_potentials
+
+
+# ----------------------------------------------------------------------------------------------------------------
 # ConditionalVariance inducing-point selector -- src/inducing_point_selectors/conditional_variance.py:27-120
 # ----------------------------------------------------------------------------------------------------------------
 def conditional_variance_select(

@@ -19,7 +19,7 @@ LIB_PATH = os.path.join(HERE, "libpls_b200.so")
 KERNEL_RBF, KERNEL_LINEAR = 0, 1
 COST_GAUSSIAN, COST_BERNOULLI, COST_POISSON, COST_MULTIMODAL, COST_STUDENT_T = range(5)
 LINK_IDENTITY, LINK_SIGMOID, LINK_PROBIT, LINK_SQUARE = range(4)
-EPI_PREDICTION, EPI_COST_DERIVATIVE, EPI_COST = range(3)
+EPI_PREDICTION, EPI_COST_DERIVATIVE, EPI_COST, EPI_COST_DERIVATIVE_AND_COST = range(4)
 NOISE_NONE, NOISE_GIVEN, NOISE_PHILOX = range(3)
 ABI_VERSION = 1
 COST_VALUE_TILE_ROWS = 128  # rows per partial sum of pls_cost_value_f64 (dense F)
@@ -68,6 +68,7 @@ SIGNATURES = {
     "pls_gram_f64": (_int, [_vp, _int, _vp, _i64, _vp, _i64, _int, _vp, _i64, _vp]),
     "pls_gemm_f64": (_int, [_vp, _int, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _vp]),
     "pls_forward_f64": (_int, [_vp, _int, _vp, _i64, _vp, _i64, _int, _vp, _i64, _i64, _int, _costp, _vp, _vp, _i64, _vp]),
+    "pls_forward_step_f64": (_int, [_vp, _int, _vp, _i64, _vp, _i64, _int, _vp, _i64, _i64, _costp, _vp, _vp, _i64, _vp, _i64, _vp]),
     "pls_backward_f64": (_int, [_vp, _int, _vp, _i64, _vp, _i64, _int, _vp, _i64, _i64, _vp, _i64, _int, _int, _vp]),
     "pls_reduce_splits_f64": (_int, [_vp, _vp, _int, _i64, _i64, _i64, _vp, _i64, _vp]),
     "pls_project_update_f64": (

@@ -180,6 +180,25 @@ int pls_forward_f64(pls_ctx* ctx, int kernel_id, const double* xa, int64_t n, co
   return check_cuda(ctx, pls::launch_gen_gemm_forward(ctx, p, (cudaStream_t)stream), "pls_forward_f64");
 }
 
+int pls_forward_step_f64(pls_ctx* ctx, int kernel_id, const double* xa, int64_t n, const double* za, int64_t m, int d,
+                         const double* w, int64_t ldw, int64_t j, const pls_cost* cost, const double* y, double* dc,
+                         int64_t lddc, double* cost_partial, int64_t ldcp, void* stream) {
+  if (!ctx) return 1;
+  if (check_kernel(ctx, kernel_id, d)) return 1;
+  if (n < 0 || m < 0 || j < 0 || !xa || !za || !w || !dc || !cost_partial || !y) return fail(ctx, "pls_forward_step_f64: bad arguments");
+  if (ldw < j || (ldw & 1) || !aligned16(w)) return fail(ctx, "pls_forward_step_f64: w must be 16-byte aligned with an even ldw >= j");
+  if (lddc < j || (lddc & 1) || !aligned16(dc)) return fail(ctx, "pls_forward_step_f64: dc must be 16-byte aligned with an even lddc >= j");
+  if (ldcp < j) return fail(ctx, "pls_forward_step_f64: ldcp < j");
+  if (check_cost(ctx, cost)) return 1;
+  pls::GenGemmParams p{};
+  p.cost = *cost;
+  p.rows_aug = xa; p.n_rows = n; p.red_aug = za; p.red_total = m; p.b = w; p.ldb = ldw; p.j = j;
+  p.sp = pls::point_stride(d); p.d = d; p.kernel_id = kernel_id; p.epilogue = PLS_EPI_COST_DERIVATIVE_AND_COST; p.splits = 1;
+  p.accumulate = 0; p.rt = pls::choose_tile_rt(ctx, j);
+  p.out = dc; p.ldo = lddc; p.out2 = cost_partial; p.ldo2 = ldcp; p.y = y;
+  return check_cuda(ctx, pls::launch_gen_gemm_forward(ctx, p, (cudaStream_t)stream), "pls_forward_step_f64");
+}
+
 int pls_backward_f64(pls_ctx* ctx, int kernel_id, const double* za, int64_t m, const double* xa, int64_t n, int d,
                      const double* dc, int64_t lddc, int64_t j, double* gp, int64_t ldg, int splits, int accumulate,
                      void* stream) {

@@ -51,12 +51,14 @@ struct Tile {
   static constexpr int SF = BJ + 2;           // row stride (doubles) of the forward epilogue's staging tile
 };
 
-// shared memory: [0, 1024) barriers + counters + exp table | STAGES x stage (1024-aligned) | STAGES x BK x sp points
+constexpr int SMEM_HEADER = 2048;  // barriers + counters + exp table [0, 1024) | y of the tile's rows [1024, 2048)
+
+// shared memory: header | STAGES x stage (1024-aligned) | STAGES x BK x sp points
 template <int RT>
 __host__ __device__ inline size_t gen_gemm_smem_bytes(int sp) {
   const size_t pipeline = (size_t)STAGES * Tile<RT>::STAGE_BYTES + sizeof(double) * (size_t)(STAGES * BK * sp);
-  const size_t staging = sizeof(double) * (size_t)(Tile<RT>::BR * Tile<RT>::SF);
-  return 1024 /* alignment slack */ + 1024 + (pipeline > staging ? pipeline : staging);
+  const size_t staging = sizeof(double) * (size_t)(Tile<RT>::BR * Tile<RT>::SF + 2 * NTHREADS);  // + cost scratch
+  return 1024 /* alignment slack */ + SMEM_HEADER + (pipeline > staging ? pipeline : staging);
 }
 
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar) {
@@ -71,9 +73,12 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, in
                "l"(tm), "r"(c0), "r"(c1), "r"(smem_u32(bar))
                : "memory");
 }
-__device__ __forceinline__ unsigned atom_add_acq_rel_shared(unsigned* addr, unsigned v) {
+// Stage-release counter.  Relaxed on purpose: a warp reaches this only after the DMMAs that consumed its LDS data of the
+// stage have issued (in-order issue: the loads have returned), so when the last warp sees the count the stage is no longer
+// being read and the tensor-map copy may overwrite it; acq_rel would put a MEMBAR in front of every release.
+__device__ __forceinline__ unsigned atom_add_shared(unsigned* addr, unsigned v) {
   unsigned old;
-  asm volatile("atom.acq_rel.cta.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(addr)), "r"(v) : "memory");
+  asm volatile("atom.relaxed.cta.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(addr)), "r"(v) : "memory");
   return old;
 }
 
@@ -87,7 +92,8 @@ __global__ void __launch_bounds__(NTHREADS, 1)
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);                      // [STAGES]
   unsigned* released = reinterpret_cast<unsigned*>(smem_raw + 64);             // [STAGES] warps done with the stage
   double* sExp = reinterpret_cast<double*>(smem_raw + 128);                    // 2^(j/64)
-  unsigned char* sB = smem_raw + 1024;                                         // [STAGES][NPR][BK rows][128 bytes], swizzled
+  double* sY = reinterpret_cast<double*>(smem_raw + 1024);                     // [BR] targets of the tile's rows (forward)
+  unsigned char* sB = smem_raw + SMEM_HEADER;                                  // [STAGES][NPR][BK rows][128 bytes], swizzled
   double* sP = reinterpret_cast<double*>(sB + STAGES * STAGE_BYTES);           // [STAGES][BK][sp]
 
   const int tid = threadIdx.x;
@@ -131,6 +137,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
   // point rows past the end of the reduction are never copied: keep them finite
   for (int i = tid; i < STAGES * BK * sp; i += NTHREADS) sP[i] = 0.0;
   if (tid < 64) sExp[tid] = kExp2Table[tid];
+  if (!BACKWARD && p.epilogue != PLS_EPI_PREDICTION && tid < BR) sY[tid] = (row0 + tid < p.n_rows) ? p.y[row0 + tid] : 0.0;
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
@@ -273,7 +280,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
       __syncwarp();
       if (lane == 0) {
         // the last warp to release the stage refills it: nobody waits
-        if (atom_add_acq_rel_shared(&released[stage], 1u) == NWARPS - 1) {
+        if (atom_add_shared(&released[stage], 1u) == NWARPS - 1) {
           released[stage] = 0;
           issue(c + STAGES);
         }
@@ -340,28 +347,48 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     // per-column sum over this tile's rows (increasing row order) of c(y_n, F[n][j]) -> out[rt][j]
     if (tid < cols_here) {
       double v = 0.0;
-      for (int r = 0; r < (int)rows_here; ++r) v += cost_value(p.cost, p.y[row0 + r], sF[r * SF + tid]);
+      for (int r = 0; r < (int)rows_here; ++r) v += cost_value(p.cost, sY[r], sF[r * SF + tid]);
       p.out[rt * p.ldo + j0 + tid] = v;
     }
     return;
   }
 
-  const bool dcost = (p.epilogue == PLS_EPI_COST_DERIVATIVE);
-  constexpr int PAIRS = BJ / 2;  // double2 per row
+  const bool dcost = (p.epilogue != PLS_EPI_PREDICTION);
+  const bool with_cost = (p.epilogue == PLS_EPI_COST_DERIVATIVE_AND_COST);
+  constexpr int PAIRS = BJ / 2;                 // double2 per row
+  constexpr int PHASES = NTHREADS / PAIRS;      // a thread keeps its column pair and visits rows phase, phase + PHASES, ...
+  const int col = 2 * (tid % PAIRS);
+  const int rphase = tid / PAIRS;
+  double csum0 = 0.0, csum1 = 0.0;              // cost of this thread's two columns over its rows, increasing row order
+  if (col < cols_here) {
 #pragma unroll 2
-  for (int idx = tid; idx < BR * PAIRS; idx += NTHREADS) {
-    const int r = idx / PAIRS;
-    const int col = 2 * (idx - r * PAIRS);
-    if (r >= rows_here || col >= cols_here) continue;
-    double2 v = *reinterpret_cast<const double2*>(sF + r * SF + col);
-    if (dcost) {
-      const double yv = p.y[row0 + r];
-      v.x = cost_derivative(p.cost, yv, v.x);
-      v.y = cost_derivative(p.cost, yv, v.y);
+    for (int r = rphase; r < (int)rows_here; r += PHASES) {
+      double2 v = *reinterpret_cast<const double2*>(sF + r * SF + col);
+      if (dcost) {
+        const double yv = sY[r];
+        if (with_cost) {
+          csum0 += cost_value(p.cost, yv, v.x);
+          csum1 += cost_value(p.cost, yv, v.y);
+        }
+        v.x = cost_derivative(p.cost, yv, v.x);
+        v.y = cost_derivative(p.cost, yv, v.y);
+      }
+      double* dst = p.out + (row0 + r) * p.ldo + j0 + col;
+      if (col + 1 < cols_here) *reinterpret_cast<double2*>(dst) = v;
+      else dst[0] = v.x;
     }
-    double* dst = p.out + (row0 + r) * p.ldo + j0 + col;
-    if (col + 1 < cols_here) *reinterpret_cast<double2*>(dst) = v;
-    else dst[0] = v.x;
+  }
+  if (with_cost) {
+    double* sC = sF + BR * SF;  // [PHASES][BJ] scratch behind the staged tile
+    sC[rphase * BJ + col] = csum0;
+    sC[rphase * BJ + col + 1] = csum1;
+    __syncthreads();
+    if (tid < cols_here) {
+      double v = 0.0;
+#pragma unroll
+      for (int ph = 0; ph < PHASES; ++ph) v += sC[ph * BJ + tid];
+      p.out2[rt * p.ldo2 + j0 + tid] = v;
+    }
   }
 }
 

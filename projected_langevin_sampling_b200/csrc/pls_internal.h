@@ -39,6 +39,8 @@ struct GenGemmParams {
   int64_t full_blocks;  // set by the launcher: complete 16-column blocks per row of the streamed matrix (ldb / 16)
   double* out;
   int64_t ldo;
+  double* out2;  // forward, PLS_EPI_COST_DERIVATIVE_AND_COST: per-row-tile cost sums (tiles x ldo2)
+  int64_t ldo2;
   const double* y;
   pls_cost cost;
 };

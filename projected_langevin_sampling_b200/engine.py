@@ -45,18 +45,32 @@ class LangevinEngine:
         self.dc = torch.zeros((self.chunk_rows, self.ldj), dtype=torch.float64, device=dev)
         self.splits = ops.backward_splits(ctx, self.chunk_rows, self.m, j)
         self.gp = torch.zeros((self.splits, self.m, self.ldj), dtype=torch.float64, device=dev)
+        self.cost_partial: Optional[torch.Tensor] = None  # (row tiles, ldj), allocated by the first gradient(with_cost=True)
+        self.tile_rows = 0
 
     # ---- pieces ------------------------------------------------------------------------------------------------------
     def _weights(self, particles: torch.Tensor) -> torch.Tensor:
         return ops.gemm(self.ctx, self.vt, particles, self.w)  # W = V~ P
 
-    def gradient(self, particles: torch.Tensor, cost: nat.PlsCost, y: torch.Tensor) -> torch.Tensor:
-        """G' = k(Z, X) d_2 c(y, k(X, Z) V~ P)  -> (M, ldj) workspace view."""
+    def gradient(self, particles: torch.Tensor, cost: nat.PlsCost, y: torch.Tensor, with_cost: bool = False) -> torch.Tensor:
+        """G' = k(Z, X) d_2 c(y, k(X, Z) V~ P)  -> (M, ldj) workspace view.  with_cost also leaves the per-row-tile cost
+        sums of the SAME forward pass in self.cost_partial (the energy potential costs no second forward)."""
         self._weights(particles)
+        if with_cost and self.cost_partial is None:
+            self.tile_rows = ops.forward_tile_rows(self.ctx, self.j)
+            tiles = sum((r1 - r0 + self.tile_rows - 1) // self.tile_rows for r0, r1 in self.chunks)
+            self.cost_partial = torch.zeros((tiles, self.ldj), dtype=torch.float64, device=self.xa.device)
+        t0 = 0
         for ci, (r0, r1) in enumerate(self.chunks):
             dc = self.dc[: r1 - r0]
-            ops.forward(self.ctx, self.kernel_id, self.xa[r0:r1], self.za, self.d, self.w, self.j, nat.EPI_COST_DERIVATIVE,
-                        dc, cost=cost, y=y[r0:r1])
+            if with_cost:
+                t1 = t0 + (r1 - r0 + self.tile_rows - 1) // self.tile_rows
+                ops.forward_step(self.ctx, self.kernel_id, self.xa[r0:r1], self.za, self.d, self.w, self.j, cost, y[r0:r1], dc,
+                                 self.cost_partial[t0:t1])
+                t0 = t1
+            else:
+                ops.forward(self.ctx, self.kernel_id, self.xa[r0:r1], self.za, self.d, self.w, self.j, nat.EPI_COST_DERIVATIVE,
+                            dc, cost=cost, y=y[r0:r1])
             ops.backward(self.ctx, self.kernel_id, self.za, self.xa[r0:r1], self.d, dc, self.j, self.gp, self.splits,
                          accumulate=ci > 0)
         ops.reduce_splits(self.ctx, self.gp, self.j, self.gm)
@@ -69,6 +83,19 @@ class LangevinEngine:
              j_global_offset: int = 0, in_place: bool = False) -> torch.Tensor:
         gm = self.gradient(particles, cost, y)
         return ops.project_update(self.ctx, self.vt, gm, particles, self.j, self.inv_lambda, eta, out, noise_mode=noise_mode,
+                                  xi=xi, seed=seed, step=step_index, j_global_offset=j_global_offset, in_place=in_place)
+
+    def energy_and_gradient(self, particles: torch.Tensor, cost: nat.PlsCost, y: torch.Tensor) -> torch.Tensor:
+        """One forward + backward: leaves G' in self.gm and returns the per-particle energy c_j + 1/2 sum_m P_mj^2 / lambda_m
+        of `particles` (J,) (PLS.calculate_energy_potential before its mean, orthonormal.py:110-126)."""
+        self.gradient(particles, cost, y, with_cost=True)
+        return ops.energy_terms(self.ctx, self.cost_partial, self.j, particles, self.inv_lambda)
+
+    def apply_update(self, particles: torch.Tensor, eta: float, out: torch.Tensor, noise_mode: int,
+                     xi: Optional[torch.Tensor] = None, seed: int = 0, step_index: int = 0, j_global_offset: int = 0,
+                     in_place: bool = False) -> torch.Tensor:
+        """The Langevin update from the gradient already in self.gm (second half of `step`)."""
+        return ops.project_update(self.ctx, self.vt, self.gm, particles, self.j, self.inv_lambda, eta, out, noise_mode=noise_mode,
                                   xi=xi, seed=seed, step=step_index, j_global_offset=j_global_offset, in_place=in_place)
 
     def prediction(self, particles: torch.Tensor) -> torch.Tensor:

@@ -88,6 +88,15 @@ def forward(ctx: nat.Context, kernel_id: int, xa: torch.Tensor, za: torch.Tensor
     return out
 
 
+def forward_step(ctx: nat.Context, kernel_id: int, xa: torch.Tensor, za: torch.Tensor, d: int, w: torch.Tensor, j: int,
+                 cost: nat.PlsCost, y: torch.Tensor, dc: torch.Tensor, cost_partial: torch.Tensor) -> None:
+    """Forward with the cost derivative AND the per-row-tile cost sums from the same F tile (pls_forward_step_f64)."""
+    ctx.check(ctx.lib.pls_forward_step_f64(ctx.handle, kernel_id, xa.data_ptr(), xa.shape[0], za.data_ptr(), za.shape[0], d,
+                                           w.data_ptr(), _ld(w), j, C.byref(cost), y.data_ptr(), dc.data_ptr(), _ld(dc),
+                                           cost_partial.data_ptr(), _ld(cost_partial), ctx.stream()))
+    ctx.launches += 1
+
+
 def backward(ctx: nat.Context, kernel_id: int, za: torch.Tensor, xa: torch.Tensor, d: int, dc: torch.Tensor, j: int,
              gp: torch.Tensor, splits: int, accumulate: bool) -> torch.Tensor:
     """gp: (splits, M, ld) storage."""

@@ -14,3 +14,22 @@ def solve(input, rhs, lhs=None):
     """gpytorch.solve: input^{-1} rhs, or lhs input^{-1} rhs (InducingPointBasis only; a "next" row)."""
     res = torch.linalg.solve(input, rhs)
     return res if lhs is None else lhs @ res
+
+
+class _Anything:
+    """Placeholder for every gpytorch class the reference merely subclasses or names in an annotation while its module
+    is imported (models.ExactGP, means.Mean, likelihoods.Likelihood, ...); never instantiated by the golden script."""
+
+    def __init__(self, *args, **kwargs):
+        pass
+
+
+class _Namespace:
+    def __getattr__(self, name):
+        return _Anything
+
+
+def __getattr__(name):  # PEP 562: gpytorch.models, gpytorch.means, gpytorch.likelihoods, gpytorch.variational, ...
+    if name.startswith("__"):
+        raise AttributeError(name)
+    return _Namespace()

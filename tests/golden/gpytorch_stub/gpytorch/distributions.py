@@ -8,3 +8,7 @@ class MultivariateNormal(torch.distributions.MultivariateNormal):
 
 class base_distributions:
     StudentT = torch.distributions.StudentT
+
+
+class Distribution:
+    """annotation-only placeholder (src/gaussian_process/svgp.py:45)"""

@@ -145,7 +145,40 @@ def selector_runs():
     print("selector:", idx.tolist()[:8], idx1.tolist()[:8])
 
 
+def train_loop_runs():
+    """experiments/trainers.py:139-162 `train_pls` (the caller of the hot path) with experiments/early_stopper.py:4-24:
+    one run that uses all its epochs and one that the EarlyStopper ends (energies appended only for accepted steps)."""
+    from experiments.trainers import train_pls  # noqa: E402  (imports src.gaussian_process: placeholders in the stub)
+
+    g = torch.Generator().manual_seed(21)
+    n, d, m, j = 80, 2, 8, 12
+    x = torch.randn(n, d, generator=g)
+    z = x[torch.randperm(n, generator=g)[:m]].clone()
+    ls = torch.tensor([0.8, 1.2])
+    kernel = make_kernel(ls, 1.4, ard=d)
+    basis = OrthonormalBasis(kernel=PLSKernel(base_kernel=kernel, approximation_samples=z), x_induce=z, x_train=x,
+                             eigenvalue_threshold=1e-6)
+    y = torch.sin(x.sum(1)) + 0.1 * torch.randn(n, generator=g)
+    y_cnt = torch.poisson(torch.full((n,), 3.0), generator=g)
+    out = dict(x=x.numpy(), z=z.numpy(), lengthscale=ls.numpy(), outputscale=1.4, y=y.numpy(), y_cnt=y_cnt.numpy(),
+               eigenvalues=basis.eigenvalues.numpy(), eigenvectors=basis.eigenvectors.numpy(), threshold=1e-6)
+    runs = {
+        "full": (GaussianCost(observation_noise=0.2, y_train=y, link_function=IdentityLinkFunction()), 40, 2e-3, 1.0, 77),
+        "stopped": (StudentTCost(degrees_of_freedom=4.0, y_train=y, link_function=IdentityLinkFunction(), scale=0.5), 400, 4e-3, 2e-2, 78),
+    }
+    for name, (cost, epochs, eta, patience, noise_seed) in runs.items():
+        pls = PLS(basis=basis, cost=cost)
+        p0 = pls.initialise_particles(number_of_particles=j, seed=3)
+        torch.manual_seed(noise_seed)
+        particles, energies = train_pls(pls=pls, particles=p0.clone(), number_of_epochs=epochs, step_size=eta,
+                                        early_stopper_patience=patience)
+        out.update({f"{name}__p0": p0.numpy(), f"{name}__p": particles.numpy(), f"{name}__energies": np.array(energies),
+                    f"{name}__epochs": epochs, f"{name}__eta": eta, f"{name}__patience": patience, f"{name}__noise_seed": noise_seed})
+        print("train_pls", name, "accepted", len(energies), "of", epochs, "E", energies[0], energies[-1])
+    np.savez(os.path.join(HERE, "train_loop_runs.npz"), **out)
+
+
 if __name__ == "__main__":
-    readme_demo()
-    one_step_all_costs()
-    selector_runs()
+    which = sys.argv[1:] or ["readme_demo", "one_step_all_costs", "selector_runs", "train_loop_runs"]
+    for name in which:
+        globals()[name]()

@@ -506,3 +506,72 @@ def test_error_behaviour_matches_reference(b200):
 
     with pytest.raises(TypeError):
         b200.OrthonormalBasis(b200.PLSKernel(Matern(), Z2), Z2, X5)
+
+
+# ---- the caller of the hot path: train_pls with the energy fused into the step's forward ---------------------------------
+@pytest.mark.parametrize("name,kind", [("full", "gaussian"), ("stopped", "student_t")])
+def test_train_pls_against_reference_run(b200, name, kind, golden_dir):
+    """projected_langevin_sampling_b200.trainers.train_pls (one forward per epoch: cost derivative and energy from the same
+    F tiles) against the reference's own experiments/trainers.py:139-162 run (tests/golden/make_golden.py)."""
+    from projected_langevin_sampling_b200.trainers import train_pls
+
+    torch.set_default_dtype(torch.float64)
+    try:
+        costs, links = _costs_mod()
+        g = np.load(os.path.join(golden_dir, "train_loop_runs.npz"))
+        x, z = torch.from_numpy(g["x"]), torch.from_numpy(g["z"])
+        kernel = b200.ScaleKernel(b200.RBFKernel(ard_num_dims=2, lengthscale=torch.from_numpy(g["lengthscale"])),
+                                  outputscale=float(g["outputscale"]))
+        eig = (torch.from_numpy(g["eigenvalues"]), torch.from_numpy(g["eigenvectors"]))
+        basis = b200.OrthonormalBasis(b200.PLSKernel(kernel, z), z, x, eigenvalue_threshold=float(g["threshold"]),
+                                      eigendecomposition=eig, verbose=False)
+        cost = (costs.GaussianCost(observation_noise=0.2, y_train=torch.from_numpy(g["y"]), link_function=links.IdentityLinkFunction())
+                if kind == "gaussian" else costs.StudentTCost(degrees_of_freedom=4.0, y_train=torch.from_numpy(g["y"]),
+                                                              link_function=links.IdentityLinkFunction(), scale=0.5))
+        pls = b200.PLS(basis, cost)
+        for on_device in (True, False):  # in place on a CUDA tensor; copied back into a host tensor
+            p0 = torch.from_numpy(g[name + "__p0"]).clone()
+            p0 = p0.cuda() if on_device else p0
+            torch.manual_seed(int(g[name + "__noise_seed"]))
+            p, energies = train_pls(pls, p0, int(g[name + "__epochs"]), float(g[name + "__eta"]), float(g[name + "__patience"]))
+            assert p is p0
+            want_e = g[name + "__energies"]
+            assert len(energies) == len(want_e)  # same epochs accepted, same stopping epoch
+            # one step agrees to 1e-10; 1e-9 over the trajectories (40 and 32 epochs) leaves room for round-off growth
+            traj_tol = 1e-9
+            assert abs(energies[0] - want_e[0]) <= 1e-10 * abs(want_e[0])
+            assert np.allclose(energies, want_e, rtol=traj_tol)
+            assert rel_err(p, torch.from_numpy(g[name + "__p"])) < traj_tol
+    finally:
+        torch.set_default_dtype(torch.float32)
+
+
+def test_train_pls_matches_stepwise_api(b200):
+    """Fused loop == the reference-shaped loop over calculate_particle_update + calculate_energy_potential, at a size with
+    several row tiles, a ragged J and both Dc chunks (row-chunked gradient and cost partials)."""
+    from projected_langevin_sampling_b200.trainers import train_pls
+
+    torch.set_default_dtype(torch.float64)
+    try:
+        costs, links = _costs_mod()
+        g = torch.Generator().manual_seed(8)
+        n, d, m, j = 700, 3, 40, 37
+        x = torch.randn(n, d, generator=g)
+        y = (torch.rand(n, generator=g) > 0.4).double()
+        z = x[:m].clone()
+        kernel = b200.ScaleKernel(b200.RBFKernel(ard_num_dims=d, lengthscale=torch.tensor([1.0, 1.4, 0.9])), outputscale=1.1)
+        basis = b200.OrthonormalBasis(b200.PLSKernel(kernel, z), z, x, eigenvalue_threshold=1e-8, verbose=False,
+                                      dc_budget_bytes=256 * 38 * 8)  # 256-row chunks -> 3 chunks
+        pls = b200.PLS(basis, costs.BernoulliCost(y_train=y, link_function=links.SigmoidLinkFunction()))
+        p0 = pls.initialise_particles(number_of_particles=j, seed=4)
+        torch.manual_seed(31)
+        p_ref, e_ref = p0.clone(), []
+        for _ in range(6):
+            p_ref += pls.calculate_particle_update(p_ref, 1e-3)
+            e_ref.append(pls.calculate_energy_potential(p_ref))
+        torch.manual_seed(31)
+        p, energies = train_pls(pls, p0.clone(), 6, 1e-3, early_stopper_patience=10.0)
+        assert np.allclose(energies, e_ref, rtol=1e-11)
+        assert rel_err(p, p_ref) < 1e-11
+    finally:
+        torch.set_default_dtype(torch.float32)

@@ -180,3 +180,17 @@ def test_gloo_world_size_2(tmp_path):
     outs = [p.communicate(timeout=240)[0] for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
+
+
+def test_early_stopper_follows_reference_rules():
+    """experiments/early_stopper.py:4-24: non-finite -> stop; no improvement accumulates simulated time; improvement resets."""
+    from projected_langevin_sampling_b200.early_stopper import EarlyStopper
+
+    s = EarlyStopper(patience=0.25)
+    assert not s.should_stop(10.0, 0.1)          # first loss becomes the minimum
+    assert not s.should_stop(10.0, 0.1)          # equal counts as "no improvement": t = 0.1
+    assert not s.should_stop(11.0, 0.1)          # t = 0.2
+    assert not s.should_stop(9.0, 0.1)           # improvement: t = 0
+    assert not s.should_stop(9.5, 0.1) and not s.should_stop(9.5, 0.1)  # t = 0.2
+    assert s.should_stop(9.5, 0.1)               # t = 0.3 >= 0.25
+    assert EarlyStopper().should_stop(float("nan"), 1e-3) and EarlyStopper().should_stop(float("inf"), 1e-3)

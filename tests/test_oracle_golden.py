@@ -280,3 +280,32 @@ def test_selector_against_reference_run(tag, golden_dir):
         assert torch.equal(z, torch.from_numpy(g[f"{tag}_z"]))
     finally:
         torch.set_default_dtype(torch.float32)
+
+
+# ---- the caller of the hot path: experiments/trainers.py:139-162 + experiments/early_stopper.py:4-24 -------------------
+@pytest.mark.parametrize("name,kind", [("full", "gaussian"), ("stopped", "student_t")])
+def test_train_loop_against_reference_run(name, kind, golden_dir):
+    """The reference's own `train_pls` was run by tests/golden/make_golden.py; `full` uses all 40 epochs, `stopped` is
+    ended by the EarlyStopper after 32 accepted epochs of 400."""
+    from oracle.pls_oracle import train_pls_oracle
+
+    torch.set_default_dtype(torch.float64)
+    try:
+        g = np.load(os.path.join(golden_dir, "train_loop_runs.npz"))
+        x, z = torch.from_numpy(g["x"]), torch.from_numpy(g["z"])
+        eig = (torch.from_numpy(g["eigenvalues"]), torch.from_numpy(g["eigenvectors"]))
+        basis = OrthonormalBasisOracle(RBFScaleKernel(torch.from_numpy(g["lengthscale"]), float(g["outputscale"])), z, x,
+                                       eigenvalue_threshold=float(g["threshold"]), eig=eig)
+        cost = (Cost("gaussian", torch.from_numpy(g["y"]), Link("identity"), observation_noise=0.2) if kind == "gaussian"
+                else Cost("student_t", torch.from_numpy(g["y"]), Link("identity"), degrees_of_freedom=4.0, scale=0.5))
+        pls = PLSOracle(basis, cost)
+        torch.manual_seed(int(g[name + "__noise_seed"]))
+        p, energies = train_pls_oracle(pls, torch.from_numpy(g[name + "__p0"]).clone(), int(g[name + "__epochs"]),
+                                       float(g[name + "__eta"]), float(g[name + "__patience"]))
+        want_e = g[name + "__energies"]
+        assert len(energies) == len(want_e)
+        assert np.allclose(energies, want_e, rtol=1e-10)
+        want_p = torch.from_numpy(g[name + "__p"])
+        assert (p - want_p).abs().max().item() <= 1e-10 * want_p.abs().max().item()
+    finally:
+        torch.set_default_dtype(torch.float32)
