@@ -40,6 +40,8 @@ UNIT = "particle-updates/s"
 WORKLOADS = {
     # name: (N, D, M, J, cost)
     "c4": dict(n=1_000_000, d=8, m=1024, j=4096, cost="gaussian", label="C4 UCI-scale synthetic regression N=1M D=8 ARD M=1024 J=4096"),
+    "c5": dict(n=20_000_000, d=16, m=4096, j=16384, cost="gaussian",
+               label="C5 large synthetic regression N=20M D=16 ARD M=4096 J=16384 (row- and particle-sharded, NCCL gradient all-reduce)"),
     "c3": dict(n=100_000, d=1, m=256, j=4096, cost="poisson", label="C3 Poisson f^2 regression N=100k D=1 M=256 J=4096"),
     "c2": dict(n=10_000, d=1, m=64, j=1024, cost="bernoulli", label="C2 1D Bernoulli classification N=10k M=64 J=1024"),
 }
@@ -67,12 +69,13 @@ def synth(workload: dict, seed: int = 0):
     return x, y, x[z_idx].clone(), ls, outputscale
 
 
-def make_pls(workload: dict, x, y, z, ls, outputscale):
+def make_pls(workload: dict, x, y, z, ls, outputscale, gradient_reduce=None):
     import projected_langevin_sampling_b200 as pkg
     from projected_langevin_sampling_b200.projected_langevin_sampling import costs, link_functions as lf
 
     kernel = pkg.ScaleKernel(pkg.RBFKernel(ard_num_dims=x.shape[1], lengthscale=ls), outputscale=outputscale)
-    basis = pkg.OrthonormalBasis(pkg.PLSKernel(kernel, z), z, x, eigenvalue_threshold=workload.get("threshold", 0.0), verbose=False)
+    basis = pkg.OrthonormalBasis(pkg.PLSKernel(kernel, z), z, x, eigenvalue_threshold=workload.get("threshold", 0.0), verbose=False,
+                                 gradient_reduce=gradient_reduce)
     if workload["cost"] == "gaussian":
         cost = costs.GaussianCost(observation_noise=0.01, y_train=y, link_function=lf.IdentityLinkFunction())
     elif workload["cost"] == "bernoulli":
@@ -291,8 +294,11 @@ def main():
     ap.add_argument("--workload", type=str, default="c4", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--n", type=int, default=None, help="override N (debugging; the line then names the reduced workload)")
-    ap.add_argument("--j", type=int, default=None)
+    ap.add_argument("--grid", type=str, default=None,
+                    help="RxC = row shards x particle shards of ONE problem (strong scaling; needs R*C == world). Default: every GPU "
+                         "advances its own J particles against replicated data (weak scaling in J, no communication)")
+    ap.add_argument("--rows", dest="n", type=int, default=None, help="override N (debugging; the line then names the reduced workload)")
+    ap.add_argument("--particles", dest="j", type=int, default=None)
     args = ap.parse_args()
     workload = dict(WORKLOADS[args.workload])
     if args.n or args.j:
@@ -323,13 +329,26 @@ def main():
     ctx = _native.context()
     t_setup = time.perf_counter()
     x, y, z, ls, outputscale = synth(workload)
-    pls = make_pls(workload, x, y, z, ls, outputscale)
+    grid = None
+    if args.grid:
+        from projected_langevin_sampling_b200.distributed import GridPlacement, gradient_allreduce, make_row_group
+
+        n_groups, j_groups = (int(v) for v in args.grid.lower().split("x"))
+        grid = GridPlacement(rank=rank, world=world, n_groups=n_groups, j_groups=j_groups)
+        row_group = make_row_group(grid) if world > 1 else None
+        r0, r1 = grid.rows(workload["n"])
+        j_off, j_end = grid.particles(workload["j"])
+        pls = make_pls(workload, x[r0:r1].contiguous(), y[r0:r1].contiguous(), z, ls, outputscale, gradient_allreduce(row_group))
+        j_local = j_end - j_off
+        del x, y
+    else:
+        pls = make_pls(workload, x, y, z, ls, outputscale)
+        j_local = workload["j"]  # weak scaling: every GPU owns J particles
+        j_off = rank * j_local
     m_k = pls.basis.approximation_dimension
-    j_local = workload["j"]  # weak scaling: every GPU owns J particles
-    j_off = rank * j_local
     lam_min = float(pls.basis.eigenvalues.min())
     eta = 1e-9 if workload["cost"] == "gaussian" else 1e-6
-    particles = pls.initialise_particles(j_local, seed=1000 + rank)
+    particles = pls.initialise_particles(j_local, seed=1000 + (grid.j_index if grid is not None else rank))  # a row group shares its particles
     torch.cuda.synchronize()
     setup_s = time.perf_counter() - t_setup
 
@@ -337,7 +356,8 @@ def main():
     timer.install()
     seed = 2024
     step_no = 0
-    for _ in range(max(args.warmup, 3)):
+    min_warmup = 1 if args.workload == "c5" else 3  # C5 steps take ~20 s each; its line is labelled accordingly
+    for _ in range(max(args.warmup, min_warmup)):
         pls.step_(particles, eta, philox=(seed, step_no, j_off))
         step_no += 1
     torch.cuda.synchronize()
@@ -369,7 +389,8 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
     ms_per_step = ms_total / args.steps
-    value = workload["j"] * world * args.steps / (ms_total * 1e-3)
+    j_global = workload["j"] if grid is not None else workload["j"] * world
+    value = j_global * args.steps / (ms_total * 1e-3)
     ksum = timer.summary()
 
     # ---- end-to-end through the reference-facing API with pinned host buffers ------------------------------------------------
@@ -403,7 +424,7 @@ def main():
             dt = float(t.item())
         torch.set_default_dtype(torch.float32)
         nbytes = m_k * j_local * 8
-        e2e = {"value": workload["j"] * world * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": 2 * nbytes,
+        e2e = {"value": j_global * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": 2 * nbytes,
                "d2h_bytes_per_step": nbytes, "steps": e2e_steps, "ms_per_step": dt / e2e_steps * 1e3,
                "what": "PLS.calculate_particle_update(particles, step_size) with particles in pinned host memory: H2D particles, "
                        "host torch.normal noise + H2D (the reference's stream), fused step, D2H delta, host add"}
@@ -430,6 +451,7 @@ def main():
         pass
     n, m, j = workload["n"], workload["m"], workload["j"]
     achieved = ksum["both"]["tflops"]
+    n_local = (grid.rows(n)[1] - grid.rows(n)[0]) if grid is not None else n
     roofline = {
         "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
         "traffic": traffic,
@@ -437,24 +459,26 @@ def main():
                         "profiles/roofline_traffic.json; the kernel is FP64-pipe bound, traffic ~= the Dc chunk written / read once",
         "kernel": "pls::gen_gemm_kernel (forward + backward roles; FP64 DMMA.8x8x4, no tcgen05 kind exists for f64)",
         "algorithmic_flops_per_step": 4.0 * n * m * j,
+        "algorithmic_flops_per_step_this_gpu": 4.0 * n_local * m * j_local,
         "per_role": {k: ksum[k] for k in ("forward", "backward") if k in ksum},
         "kernel_share_of_step": ksum["both"]["ms_total"] / ms_total if world == 1 else None,
         "peak_source": ("cuBLAS DGEMM via torch.matmul fp64 8192^3 measured on this pool's B200 "
                         f"(profiles/fp64_peak_r01.json sustained={peak_file}, live best-of-6 in this run={peak_live:.2f}); "
                         "MEASURED_PEAKS.json holds no FP64 figure; FP64 pipe peak from tools/fp64_microbench = 37.1 TFLOP/s"),
-        "step_tflops": 4.0 * n * m * j / (ms_per_step * 1e-3) * 1e-12,
+        "step_tflops_per_gpu": 4.0 * n_local * m * j_local / (ms_per_step * 1e-3) * 1e-12,
     }
     cpu = None
     if not args.no_cpu_baseline:
         r = cpu_reference_sample(workload, steps=2, warmup=1)
         cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, min_warmup),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if grid is not None else "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": workload["label"], "N": n, "D": workload["d"], "M": m, "M_k": m_k, "J_per_gpu": j,
-                   "J_global": j * world, "cost": workload["cost"], "step_size": eta, "lambda_min": lam_min,
-                   "noise": "Philox4x32-10 on device keyed on global (row, particle)", "parallelism": f"particle-sharded x{world}",
+        "config": {"workload": workload["label"], "N": n, "D": workload["d"], "M": m, "M_k": m_k, "J_per_gpu": j_local,
+                   "J_global": j_global, "rows_per_gpu": n_local, "cost": workload["cost"], "step_size": eta, "lambda_min": lam_min,
+                   "noise": "Philox4x32-10 on device keyed on global (row, particle)", "parallelism": (f"grid {args.grid}: rows sharded x{grid.n_groups} (NCCL all-reduce of the M x J_local gradient per step), "
+                                   f"particles sharded x{grid.j_groups}") if grid is not None else f"particle-sharded x{world}",
                    "l2": "per-step working set (Dc chunk 8 GiB written+read) exceeds the 126 MB L2; no flush needed",
                    "particles_finite": finite, "setup_s": setup_s},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,

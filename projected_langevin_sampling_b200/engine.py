@@ -47,6 +47,7 @@ class LangevinEngine:
         self.gp = torch.zeros((self.splits, self.m, self.ldj), dtype=torch.float64, device=dev)
         self.cost_partial: Optional[torch.Tensor] = None  # (row tiles, ldj), allocated by the first gradient(with_cost=True)
         self.tile_rows = 0
+        self._zeros: Optional[torch.Tensor] = None
 
     # ---- pieces ------------------------------------------------------------------------------------------------------
     def _weights(self, particles: torch.Tensor) -> torch.Tensor:
@@ -89,7 +90,17 @@ class LangevinEngine:
         """One forward + backward: leaves G' in self.gm and returns the per-particle energy c_j + 1/2 sum_m P_mj^2 / lambda_m
         of `particles` (J,) (PLS.calculate_energy_potential before its mean, orthonormal.py:110-126)."""
         self.gradient(particles, cost, y, with_cost=True)
-        return ops.energy_terms(self.ctx, self.cost_partial, self.j, particles, self.inv_lambda)
+        if self.gradient_reduce is None:
+            return ops.energy_terms(self.ctx, self.cost_partial, self.j, particles, self.inv_lambda)
+        # rows are sharded: the cost sums are partial over this rank's rows (summed over the row group), the prior term is not
+        c = ops.energy_terms(self.ctx, self.cost_partial, self.j, None, None)
+        self.gradient_reduce(c)
+        return c + ops.energy_terms(self.ctx, self._zero_row(), self.j, particles, self.inv_lambda)
+
+    def _zero_row(self) -> torch.Tensor:
+        if self._zeros is None:
+            self._zeros = torch.zeros((1, self.ldj), dtype=torch.float64, device=self.xa.device)
+        return self._zeros
 
     def apply_update(self, particles: torch.Tensor, eta: float, out: torch.Tensor, noise_mode: int,
                      xi: Optional[torch.Tensor] = None, seed: int = 0, step_index: int = 0, j_global_offset: int = 0,
@@ -121,7 +132,10 @@ class LangevinEngine:
         return part
 
     def cost(self, particles: torch.Tensor, cost: nat.PlsCost, y: torch.Tensor) -> torch.Tensor:
-        return ops.energy_terms(self.ctx, self.cost_partials(particles, cost, y), self.j, None, None)
+        c = ops.energy_terms(self.ctx, self.cost_partials(particles, cost, y), self.j, None, None)
+        if self.gradient_reduce is not None:  # rows sharded: sum the per-particle cost over the row group
+            self.gradient_reduce(c)
+        return c
 
     def backproject_update(self, particles: torch.Tensor, cost_derivative: torch.Tensor, eta: float, out: torch.Tensor,
                            noise_mode: int, xi: Optional[torch.Tensor]) -> torch.Tensor:
