@@ -152,6 +152,14 @@ def test_generated_operand_gemm_tile_shapes(ctx, rt, n, m, d, j, ldw, lddc):
         ops.forward(ctx, nat.KERNEL_RBF, xa, za, d, w_store, j, nat.EPI_COST, part, cost=cost, y=y)
         want_c = ((want_f - y[:, None]) ** 2 / (2 * 0.3)).sum(0)
         assert (part[:, :j].sum(0) - want_c).abs().max().item() < 1e-11 * max(1.0, want_c.abs().max().item())
+        # fused epilogue (pls_forward_step_f64): the cost derivative and the cost sums from one pass over the same F tile
+        dc_out = torch.full((n, ldw), 9.0, dtype=torch.float64).cuda()
+        part2 = torch.zeros(tiles, ldw, dtype=torch.float64).cuda()
+        ops.forward_step(ctx, nat.KERNEL_RBF, xa, za, d, w_store, j, cost, y, dc_out, part2)
+        want_dc = (want_f - y[:, None]) / 0.3
+        assert (dc_out[:, :j] - want_dc).abs().max().item() < 1e-11 * max(1.0, want_dc.abs().max().item())
+        assert (dc_out[:, j:] == 9.0).all()
+        assert (part2[:, :j].sum(0) - want_c).abs().max().item() < 1e-11 * max(1.0, want_c.abs().max().item())
         dc_store = torch.randn(n, lddc, generator=g, dtype=torch.float64).cuda()
         want_g = k_xz.T @ dc_store[:, :j]
         for splits in (1, 2, 5):
