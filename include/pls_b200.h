@@ -209,6 +209,31 @@ int pls_cv_select_f64(pls_ctx* ctx, int kernel_id, const double* xp_aug, int64_t
                       double jitter, double threshold, int has_threshold, double* ci, double* di, double* scratch,
                       int64_t* indices_out, int* n_selected_out, void* stream);
 
+/* ---- the selector with the points sharded by rows over several GPUs -------------------------------------------- */
+/* Rank r holds rows [n_offset, n_offset + n_local) of the permuted point set, its slice of C ((m-1) x n_local) and of d.
+ * Per pivot every rank publishes ONE candidate record (pls_cv_candidate_doubles(d, m) doubles: value, global index,
+ * local sum of d, the candidate's augmented point and its column of C); the HOST all-gathers the records of all ranks
+ * (torch.distributed / NCCL, the only exchange: <= (m + SP + 4) doubles per rank and pivot) and every rank picks the same
+ * pivot from them with the single-GPU rules (ties by GLOBAL index), so the selected indices equal pls_cv_select_f64's.
+ *   pls_cv_shard_begin_f64 : d = diag + jitter; candidate for pivot 0
+ *   [all-gather]  pls_cv_shard_pick_f64(slot = 0)
+ *   for i in 0 .. m-2:  pls_cv_shard_update_f64(iter = i)  (rank-1 update with the published pivot; candidate for pivot i+1)
+ *                       [all-gather]  pls_cv_shard_pick_f64(slot = i + 1)
+ *   pls_cv_shard_finish    : synchronises, returns how many pivots were chosen
+ * indices_out: m int64 GLOBAL positions in the permuted order, pre-filled with the sentinel n_total by the caller.
+ * scratch: pls_cv_shard_scratch_doubles(n_local, d, m) doubles, private to the rank. */
+int64_t pls_cv_shard_scratch_doubles(int64_t n_local, int d, int m);
+int64_t pls_cv_candidate_doubles(int d, int m);
+int pls_cv_shard_begin_f64(pls_ctx* ctx, int kernel_id, const double* xa_local, int64_t n_local, int64_t n_offset, int d,
+                           double kdiag, int m, double jitter, double* di, double* scratch, double* candidate, void* stream);
+int pls_cv_shard_pick_f64(pls_ctx* ctx, const double* candidates, int world, int slot, int d, int m, double threshold,
+                          int has_threshold, int64_t n_local, int64_t n_offset, double* scratch, int64_t* indices_out,
+                          void* stream);
+int pls_cv_shard_update_f64(pls_ctx* ctx, int kernel_id, const double* xa_local, int64_t n_local, int64_t n_offset, int d,
+                            int iter, int m, double jitter, double* ci, double* di, double* scratch, double* candidate,
+                            void* stream);
+int pls_cv_shard_finish(pls_ctx* ctx, const double* scratch, int* n_selected_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -81,6 +81,12 @@ SIGNATURES = {
     "pls_philox_normal_f64": (_int, [_vp, _u64, _u64, _i64, _i64, _i64, _vp, _i64, _vp]),
     "pls_gram_exp_f64": (_int, [_vp, _vp, _i64, _int, _vp, _vp]),
     "pls_cv_scratch_doubles": (_i64, [_i64]),
+    "pls_cv_shard_scratch_doubles": (_i64, [_i64, _int, _int]),
+    "pls_cv_candidate_doubles": (_i64, [_int, _int]),
+    "pls_cv_shard_begin_f64": (_int, [_vp, _int, _vp, _i64, _i64, _int, _dbl, _int, _dbl, _vp, _vp, _vp, _vp]),
+    "pls_cv_shard_pick_f64": (_int, [_vp, _vp, _int, _int, _int, _int, _dbl, _int, _i64, _i64, _vp, _vp, _vp]),
+    "pls_cv_shard_update_f64": (_int, [_vp, _int, _vp, _i64, _i64, _int, _int, _int, _dbl, _vp, _vp, _vp, _vp, _vp]),
+    "pls_cv_shard_finish": (_int, [_vp, _vp, C.POINTER(_int), _vp]),
     "pls_cv_select_f64": (_int, [_vp, _int, _vp, _i64, _int, _dbl, _int, _dbl, _dbl, _int, _vp, _vp, _vp, _vp, C.POINTER(_int), _vp]),
 }
 

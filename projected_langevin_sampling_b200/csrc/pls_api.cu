@@ -296,4 +296,45 @@ int pls_cv_select_f64(pls_ctx* ctx, int kernel_id, const double* xp_aug, int64_t
                     "pls_cv_select_f64");
 }
 
+int64_t pls_cv_shard_scratch_doubles(int64_t n_local, int d, int m) {
+  return (n_local < 0 || d < 1 || d > pls::MAX_D || m < 2) ? 0 : pls::cv_shard_scratch_doubles(n_local, d, m);
+}
+int64_t pls_cv_candidate_doubles(int d, int m) { return (d < 1 || d > pls::MAX_D || m < 2) ? 0 : pls::cv_candidate_doubles(d, m); }
+
+int pls_cv_shard_begin_f64(pls_ctx* ctx, int kernel_id, const double* xa_local, int64_t n_local, int64_t n_offset, int d,
+                           double kdiag, int m, double jitter, double* di, double* scratch, double* candidate, void* stream) {
+  if (!ctx) return 1;
+  if (check_kernel(ctx, kernel_id, d)) return 1;
+  if (m < 2) return fail(ctx, "pls_cv_shard_begin_f64: Must have at least 2 inducing points");
+  if (n_local < 0 || n_offset < 0 || !scratch || !candidate || (n_local > 0 && (!xa_local || !di)))
+    return fail(ctx, "pls_cv_shard_begin_f64: bad arguments");
+  return check_cuda(ctx, pls::cv_shard_begin(kernel_id, xa_local, n_local, n_offset, d, kdiag, m, jitter, di, scratch, candidate,
+                                             (cudaStream_t)stream), "pls_cv_shard_begin_f64");
+}
+
+int pls_cv_shard_pick_f64(pls_ctx* ctx, const double* candidates, int world, int slot, int d, int m, double threshold,
+                          int has_threshold, int64_t n_local, int64_t n_offset, double* scratch, int64_t* indices_out, void* stream) {
+  if (!ctx) return 1;
+  if (!candidates || world < 1 || slot < 0 || slot >= m || d < 1 || d > pls::MAX_D || !scratch || !indices_out)
+    return fail(ctx, "pls_cv_shard_pick_f64: bad arguments");
+  return check_cuda(ctx, pls::cv_shard_pick(candidates, world, slot, d, m, threshold, has_threshold, n_local, n_offset, scratch,
+                                            indices_out, (cudaStream_t)stream), "pls_cv_shard_pick_f64");
+}
+
+int pls_cv_shard_update_f64(pls_ctx* ctx, int kernel_id, const double* xa_local, int64_t n_local, int64_t n_offset, int d, int iter,
+                            int m, double jitter, double* ci, double* di, double* scratch, double* candidate, void* stream) {
+  if (!ctx) return 1;
+  if (check_kernel(ctx, kernel_id, d)) return 1;
+  if (iter < 0 || iter >= m - 1 || n_local < 0 || !scratch || !candidate || (n_local > 0 && (!xa_local || !ci || !di)))
+    return fail(ctx, "pls_cv_shard_update_f64: bad arguments");
+  return check_cuda(ctx, pls::cv_shard_update(kernel_id, xa_local, n_local, n_offset, d, iter, m, jitter, ci, di, scratch, candidate,
+                                              (cudaStream_t)stream), "pls_cv_shard_update_f64");
+}
+
+int pls_cv_shard_finish(pls_ctx* ctx, const double* scratch, int* n_selected_out, void* stream) {
+  if (!ctx) return 1;
+  if (!scratch || !n_selected_out) return fail(ctx, "pls_cv_shard_finish: NULL argument");
+  return check_cuda(ctx, pls::cv_shard_finish(scratch, n_selected_out, (cudaStream_t)stream), "pls_cv_shard_finish");
+}
+
 }  // extern "C"

@@ -55,4 +55,15 @@ cudaError_t run_cv_select(const pls_ctx* ctx, int kernel_id, const double* xp_au
                           double jitter, double threshold, int has_threshold, double* ci, double* di, double* scratch,
                           int64_t* indices_out, int* n_selected_out, cudaStream_t stream);
 
+// row-sharded selector (one candidate record per rank and pivot; the host all-gathers the records between the calls)
+int64_t cv_shard_scratch_doubles(int64_t n_local, int d, int m);
+int64_t cv_candidate_doubles(int d, int m);
+cudaError_t cv_shard_begin(int kernel_id, const double* xa, int64_t n_local, int64_t n_offset, int d, double kdiag, int m,
+                           double jitter, double* di, double* scratch, double* cand, cudaStream_t stream);
+cudaError_t cv_shard_pick(const double* cands, int world, int slot, int d, int m, double threshold, int has_threshold,
+                          int64_t n_local, int64_t n_offset, double* scratch, int64_t* indices, cudaStream_t stream);
+cudaError_t cv_shard_update(int kernel_id, const double* xa, int64_t n_local, int64_t n_offset, int d, int iter, int m,
+                            double jitter, double* ci, double* di, double* scratch, double* cand, cudaStream_t stream);
+cudaError_t cv_shard_finish(const double* scratch, int* n_selected_out, cudaStream_t stream);
+
 }  // namespace pls

@@ -207,6 +207,160 @@ __global__ void __launch_bounds__(CV_THREADS) cv_update_kernel(int kernel_id, co
   block_reduce_store(best, sum, /*tie_low=*/false, parts + 3 * (int64_t)blockIdx.x);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Row-sharded selector: every rank holds rows [n_offset, n_offset + n_local) of the permuted points.  Per pivot each rank
+// publishes ONE fixed-size candidate record; the host all-gathers the records (the only exchange) and every rank picks
+// the same pivot from them.  Scratch layout: header | pivot record (x_aug row, then c[0:m-1, pivot]) | parts | taken.
+//   candidate record: [0] value, [1] global index (int64 bits, -1 = none), [2] local sum(d), [3] unused,
+//                     [4, 4+SP) the candidate's augmented point, [4+SP, 4+SP+m-1) its column of C (rows filled so far)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) cv_candidate_kernel(const double* __restrict__ parts, int64_t nparts, int tie_low,
+                                                            const double* __restrict__ xa, int64_t n_local, int64_t n_offset,
+                                                            int sp, const double* __restrict__ ci, int filled,
+                                                            const double* __restrict__ scratch, double* __restrict__ cand) {
+  const long long* hdr_i = reinterpret_cast<const long long*>(scratch);
+  __shared__ double s_val[1024];
+  __shared__ long long s_idx[1024];
+  __shared__ double s_sum[1024];
+  const bool stopped = hdr_i[2] != 0;
+  Best best = {-1.0, -1};
+  double sum = 0.0;
+  if (!stopped) {
+    for (int64_t b = threadIdx.x; b < nparts; b += 1024) {
+      Best o = {parts[3 * b], __double_as_longlong(parts[3 * b + 1])};
+      best = better(best, o, tie_low != 0);
+      sum += parts[3 * b + 2];
+    }
+  }
+  s_val[threadIdx.x] = best.val;
+  s_idx[threadIdx.x] = best.idx;
+  s_sum[threadIdx.x] = sum;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      Best a = {s_val[threadIdx.x], s_idx[threadIdx.x]};
+      Best b = {s_val[threadIdx.x + o], s_idx[threadIdx.x + o]};
+      a = better(a, b, tie_low != 0);
+      s_val[threadIdx.x] = a.val;
+      s_idx[threadIdx.x] = a.idx;
+      s_sum[threadIdx.x] += s_sum[threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  const long long loc = s_idx[0];
+  if (threadIdx.x == 0) {
+    cand[0] = s_val[0];
+    cand[1] = __longlong_as_double(loc >= 0 ? loc + n_offset : -1LL);
+    cand[2] = s_sum[0];
+    cand[3] = 0.0;
+  }
+  if (loc >= 0) {
+    for (int k = threadIdx.x; k < sp; k += 1024) cand[4 + k] = xa[loc * sp + k];
+    for (int l = threadIdx.x; l < filled; l += 1024) cand[4 + sp + l] = ci[(int64_t)l * n_local + loc];
+  }
+}
+
+// one block: choose the pivot for `slot` among the ranks' candidates, publish it in the scratch header + pivot record
+__global__ void __launch_bounds__(256) cv_pick_kernel(const double* __restrict__ cands, int world, int64_t rec, int slot,
+                                                      int first, int sp, int filled, double threshold, int has_threshold,
+                                                      int64_t n_local, int64_t n_offset, double* __restrict__ scratch,
+                                                      unsigned char* __restrict__ taken, int64_t* __restrict__ indices) {
+  long long* hdr_i = reinterpret_cast<long long*>(scratch);
+  if (!first && hdr_i[2] != 0) return;  // already stopped
+  __shared__ int s_win;
+  if (threadIdx.x == 0) {
+    Best best = {-1.0, -1};
+    int win = -1;
+    double sum = 0.0;
+    for (int r = 0; r < world; ++r) {  // fixed rank order: the same decision on every rank
+      const double* c = cands + (int64_t)r * rec;
+      Best o = {c[0], __double_as_longlong(c[1])};
+      const Best nb = better(best, o, first != 0);
+      if (nb.idx != best.idx) win = r;
+      best = nb;
+      sum += c[2];
+    }
+    s_win = win;
+    if (best.idx >= 0) {
+      scratch[0] = sqrt(best.val);
+      hdr_i[1] = best.idx;
+      indices[slot] = best.idx;
+      if (best.idx >= n_offset && best.idx < n_offset + n_local) taken[best.idx - n_offset] = 1;
+      hdr_i[3] = slot + 1;
+    } else {
+      hdr_i[2] = 1;  // nothing left to choose
+    }
+    scratch[4] = sum;
+    if (!first && has_threshold && sum < threshold) hdr_i[2] = 1;  // conditional_variance.py:111-116
+  }
+  __syncthreads();
+  const int win = s_win;
+  if (win < 0) return;
+  const double* c = cands + (int64_t)win * rec + 4;
+  double* pivot = scratch + CV_HDR;
+  for (int k = threadIdx.x; k < sp + filled; k += 256) pivot[k] = c[k];
+}
+
+__global__ void __launch_bounds__(CV_THREADS) cv_update_sharded_kernel(int kernel_id, const double* __restrict__ xa, int64_t n,
+                                                                       int64_t n_offset, int d, int sp, int iter, double jitter,
+                                                                       double* __restrict__ ci, double* __restrict__ di,
+                                                                       const unsigned char* __restrict__ taken,
+                                                                       const double* __restrict__ scratch,
+                                                                       double* __restrict__ parts) {
+  const long long* hdr_i = reinterpret_cast<const long long*>(scratch);
+  if (hdr_i[2] != 0) return;
+  __shared__ double s_cj[CV_CJ_CHUNK];
+  __shared__ double s_piv[32];
+  const int64_t piv = hdr_i[1];  // global index
+  const double dj = scratch[0];
+  const double* pivot = scratch + CV_HDR;  // [x_aug row | c[0:iter, pivot]]
+  const int64_t i = (int64_t)blockIdx.x * CV_THREADS + threadIdx.x;
+  if (threadIdx.x < sp) s_piv[threadIdx.x] = pivot[threadIdx.x];
+
+  double dot = 0.0;  // same order of accumulation as cv_update_kernel: results are identical to the unsharded selector
+  for (int l0 = 0; l0 < iter; l0 += CV_CJ_CHUNK) {
+    const int lc = (iter - l0 < CV_CJ_CHUNK) ? (iter - l0) : CV_CJ_CHUNK;
+    __syncthreads();
+    for (int l = threadIdx.x; l < lc; l += CV_THREADS) s_cj[l] = pivot[sp + l0 + l];
+    __syncthreads();
+    if (i < n) {
+      const double* col = ci + (int64_t)l0 * n + i;
+      int l = 0;
+      for (; l + 4 <= lc; l += 4) {
+        const double c0 = col[(int64_t)(l + 0) * n], c1 = col[(int64_t)(l + 1) * n];
+        const double c2 = col[(int64_t)(l + 2) * n], c3 = col[(int64_t)(l + 3) * n];
+        dot = fma(s_cj[l + 0], c0, dot);
+        dot = fma(s_cj[l + 1], c1, dot);
+        dot = fma(s_cj[l + 2], c2, dot);
+        dot = fma(s_cj[l + 3], c3, dot);
+      }
+      for (; l < lc; ++l) dot = fma(s_cj[l], col[(int64_t)l * n], dot);
+    }
+  }
+  __syncthreads();
+
+  Best best = {-1.0, -1};
+  double sum = 0.0;
+  if (i < n) {
+    double col = aug_dot(xa + i * sp, s_piv, d);
+    if (kernel_id == PLS_KERNEL_RBF) col = gram_exp(col);
+    col = __ddiv_rn(rint(__dmul_rn(col, 1e20)), 1e20);
+    if (i + n_offset == piv) col += jitter;
+    const double e = (col - dot) / dj;
+    ci[(int64_t)iter * n + i] = e;
+    double dn = di[i] - e * e;
+    dn = fmax(dn, 0.0);
+    di[i] = dn;
+    sum = dn;
+    if (!taken[i]) {
+      best.val = dn;
+      best.idx = i;
+    }
+  }
+  block_reduce_store(best, sum, /*tie_low=*/false, parts + 3 * (int64_t)blockIdx.x);
+}
+
 }  // namespace
 
 int64_t cv_scratch_doubles(int64_t n) {
@@ -234,6 +388,70 @@ cudaError_t run_cv_select(const pls_ctx* ctx, int kernel_id, const double* xp_au
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   long long nsel = 0;
   if ((e = cudaMemcpyAsync(&nsel, reinterpret_cast<long long*>(scratch) + 3, sizeof(long long), cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return e;
+  if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return e;
+  *n_selected_out = (int)nsel;
+  return cudaSuccess;
+}
+
+// ---- row-sharded selector: host side ----------------------------------------------------------------------------------
+int64_t cv_shard_scratch_doubles(int64_t n_local, int d, int m) {
+  const int64_t nb = (n_local + CV_THREADS - 1) / CV_THREADS;
+  return CV_HDR + point_stride(d) + m + 3 * (nb > 0 ? nb : 1) + (n_local + 7) / 8 + 1;
+}
+int64_t cv_candidate_doubles(int d, int m) { return 4 + point_stride(d) + m; }
+
+namespace {
+struct ShardLayout {
+  int sp;
+  int64_t nb;
+  double* parts;
+  unsigned char* taken;
+};
+ShardLayout shard_layout(double* scratch, int64_t n_local, int d, int m) {
+  ShardLayout l;
+  l.sp = point_stride(d);
+  l.nb = (n_local + CV_THREADS - 1) / CV_THREADS;
+  l.parts = scratch + CV_HDR + l.sp + m;
+  l.taken = reinterpret_cast<unsigned char*>(l.parts + 3 * (l.nb > 0 ? l.nb : 1));
+  return l;
+}
+}  // namespace
+
+cudaError_t cv_shard_begin(int kernel_id, const double* xa, int64_t n_local, int64_t n_offset, int d, double kdiag, int m,
+                           double jitter, double* di, double* scratch, double* cand, cudaStream_t stream) {
+  const ShardLayout l = shard_layout(scratch, n_local, d, m);
+  if (l.nb > 2147483647LL) return cudaErrorInvalidConfiguration;
+  cudaError_t e;
+  if ((e = cudaMemsetAsync(scratch, 0, sizeof(double) * (CV_HDR + l.sp + m), stream)) != cudaSuccess) return e;
+  if (l.nb > 0)
+    cv_init_kernel<<<(unsigned)l.nb, CV_THREADS, 0, stream>>>(kernel_id, xa, n_local, d, l.sp, kdiag, jitter, di, l.taken, l.parts);
+  cv_candidate_kernel<<<1, 1024, 0, stream>>>(l.parts, l.nb, /*tie_low=*/1, xa, n_local, n_offset, l.sp, nullptr, 0, scratch, cand);
+  return cudaGetLastError();
+}
+
+cudaError_t cv_shard_pick(const double* cands, int world, int slot, int d, int m, double threshold, int has_threshold,
+                          int64_t n_local, int64_t n_offset, double* scratch, int64_t* indices, cudaStream_t stream) {
+  const ShardLayout l = shard_layout(scratch, n_local, d, m);
+  const int filled = slot > 0 ? slot : 0;  // rows of C that exist when pivot `slot` is chosen
+  cv_pick_kernel<<<1, 256, 0, stream>>>(cands, world, cv_candidate_doubles(d, m), slot, slot == 0, l.sp, filled, threshold,
+                                        has_threshold, n_local, n_offset, scratch, l.taken, indices);
+  return cudaGetLastError();
+}
+
+cudaError_t cv_shard_update(int kernel_id, const double* xa, int64_t n_local, int64_t n_offset, int d, int iter, int m,
+                            double jitter, double* ci, double* di, double* scratch, double* cand, cudaStream_t stream) {
+  const ShardLayout l = shard_layout(scratch, n_local, d, m);
+  if (l.nb > 0)
+    cv_update_sharded_kernel<<<(unsigned)l.nb, CV_THREADS, 0, stream>>>(kernel_id, xa, n_local, n_offset, d, l.sp, iter, jitter, ci,
+                                                                        di, l.taken, scratch, l.parts);
+  cv_candidate_kernel<<<1, 1024, 0, stream>>>(l.parts, l.nb, /*tie_low=*/0, xa, n_local, n_offset, l.sp, ci, iter + 1, scratch, cand);
+  return cudaGetLastError();
+}
+
+cudaError_t cv_shard_finish(const double* scratch, int* n_selected_out, cudaStream_t stream) {
+  long long nsel = 0;
+  cudaError_t e;
+  if ((e = cudaMemcpyAsync(&nsel, reinterpret_cast<const long long*>(scratch) + 3, sizeof(long long), cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return e;
   if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return e;
   *n_selected_out = (int)nsel;
   return cudaSuccess;

@@ -200,3 +200,67 @@ def cv_select(ctx: nat.Context, kernel_id: int, xp_aug: torch.Tensor, d: int, kd
                                         C.byref(nsel), ctx.stream()))
     ctx.launches += 2 * m
     return indices, int(nsel.value)
+
+
+class ShardedSelectorState:
+    """One rank's workspaces of the row-sharded ConditionalVariance selector (pls_cv_shard_*)."""
+
+    def __init__(self, ctx: nat.Context, kernel_id: int, xa_local: torch.Tensor, n_offset: int, n_total: int, d: int, kdiag: float,
+                 m: int, jitter: float, threshold: Optional[float]):
+        self.ctx, self.kernel_id, self.xa, self.n_offset, self.d, self.m = ctx, kernel_id, xa_local, int(n_offset), d, m
+        self.kdiag, self.jitter = float(kdiag), float(jitter)
+        self.threshold, self.has_threshold = (float(threshold), 1) if threshold is not None else (0.0, 0)
+        self.n_local = xa_local.shape[0]
+        dev = xa_local.device
+        self.ci = torch.empty((m - 1, max(self.n_local, 1)), dtype=F64, device=dev)
+        self.di = torch.empty((max(self.n_local, 1),), dtype=F64, device=dev)
+        self.scratch = torch.zeros((int(ctx.lib.pls_cv_shard_scratch_doubles(self.n_local, d, m)),), dtype=F64, device=dev)
+        self.record = int(ctx.lib.pls_cv_candidate_doubles(d, m))
+        self.candidate = torch.zeros((self.record,), dtype=F64, device=dev)
+        self.indices = torch.full((m,), int(n_total), dtype=torch.int64, device=dev)  # sentinel N (conditional_variance.py:63)
+
+    def begin(self) -> torch.Tensor:
+        c = self.ctx
+        c.check(c.lib.pls_cv_shard_begin_f64(c.handle, self.kernel_id, self.xa.data_ptr(), self.n_local, self.n_offset, self.d,
+                                             self.kdiag, self.m, self.jitter, self.di.data_ptr(), self.scratch.data_ptr(),
+                                             self.candidate.data_ptr(), c.stream()))
+        c.launches += 2
+        return self.candidate
+
+    def pick(self, candidates: torch.Tensor, slot: int) -> None:
+        c = self.ctx
+        world = candidates.numel() // self.record
+        c.check(c.lib.pls_cv_shard_pick_f64(c.handle, candidates.data_ptr(), world, slot, self.d, self.m, self.threshold,
+                                            self.has_threshold, self.n_local, self.n_offset, self.scratch.data_ptr(),
+                                            self.indices.data_ptr(), c.stream()))
+        c.launches += 1
+
+    def update(self, iteration: int) -> torch.Tensor:
+        c = self.ctx
+        c.check(c.lib.pls_cv_shard_update_f64(c.handle, self.kernel_id, self.xa.data_ptr(), self.n_local, self.n_offset, self.d,
+                                              iteration, self.m, self.jitter, self.ci.data_ptr(), self.di.data_ptr(),
+                                              self.scratch.data_ptr(), self.candidate.data_ptr(), c.stream()))
+        c.launches += 2
+        return self.candidate
+
+    def finish(self) -> int:
+        c = self.ctx
+        nsel = C.c_int(0)
+        c.check(c.lib.pls_cv_shard_finish(c.handle, self.scratch.data_ptr(), C.byref(nsel), c.stream()))
+        return int(nsel.value)
+
+
+def cv_select_sharded(states: Sequence[ShardedSelectorState], gather) -> Tuple[torch.Tensor, int]:
+    """Drives the sharded selector.  `states` are the ranks handled by THIS process (one in production; several when a
+    test emulates the ranks on one GPU); `gather(list of this process's candidate records)` returns all ranks' records
+    concatenated in rank order (torch.distributed.all_gather_into_tensor in production)."""
+    m = states[0].m
+    cands = gather([s.begin() for s in states])
+    for s in states:
+        s.pick(cands, 0)
+    for i in range(m - 1):
+        cands = gather([s.update(i) for s in states])
+        for s in states:
+            s.pick(cands, i + 1)
+    nsel = [s.finish() for s in states]
+    return states[0].indices, nsel[0]

@@ -193,3 +193,27 @@ def test_non_finite_cost_derivative_stays_in_its_column(ctx):
     ops.reduce_splits(ctx, gp, j, out)
     finite_cols = torch.isfinite(out).all(0)
     assert not finite_cols[7] and finite_cols[torch.arange(j).cuda() != 7].all()
+
+
+@pytest.mark.parametrize("bounds", [[0, 1700, 3000], [0, 1, 1, 2999, 3000], [0, 3000]])
+@pytest.mark.parametrize("threshold", [0.0, 2400.0])
+def test_row_sharded_selector_equals_unsharded(ctx, bounds, threshold):
+    """pls_cv_shard_* with the ranks emulated on one GPU (the all-gather is a concatenation): uneven shards, a one-row
+    shard and an EMPTY shard; the indices and the early-stop count must equal pls_cv_select_f64's."""
+    from projected_langevin_sampling_b200 import _native as nat, ops
+
+    g = torch.Generator().manual_seed(17)
+    n, d, m = 3000, 5, 40
+    x = torch.randn(n, d, generator=g, dtype=torch.float64).cuda()
+    x[100] = x[2500]  # an exact duplicate: a tie that the GLOBAL-index rule must resolve identically across shards
+    inv_ls = [0.5, 0.6, 0.7, 0.4, 0.45]
+    centre = x.mean(0).tolist()
+    xa = ops.prepare_points(ctx, nat.KERNEL_RBF, x, inv_ls, centre, 0.5 * float(np.log(1.3)))
+    want_idx, want_n = ops.cv_select(ctx, nat.KERNEL_RBF, xa, d, 1.3, m, 1e-12, threshold)
+    states = [ops.ShardedSelectorState(ctx, nat.KERNEL_RBF, xa[a:b].contiguous(), a, n, d, 1.3, m, 1e-12, threshold)
+              for a, b in zip(bounds[:-1], bounds[1:])]
+    got_idx, got_n = ops.cv_select_sharded(states, lambda recs: torch.cat(recs))
+    assert got_n == want_n and (threshold == 0.0) == (want_n == m)
+    assert torch.equal(got_idx, want_idx)
+    for s in states[1:]:  # every rank ends with the same answer
+        assert torch.equal(s.indices, got_idx)

@@ -26,10 +26,10 @@ from projected_langevin_sampling_b200.trainers import train_pls  # noqa: E402
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--grid", type=str, default="2x1", help="row shards x particle shards")
-    ap.add_argument("--n", type=int, default=30000)
-    ap.add_argument("--m", type=int, default=128)
-    ap.add_argument("--d", type=int, default=4)
-    ap.add_argument("--j", type=int, default=512)
+    ap.add_argument("--points", dest="n", type=int, default=30000)
+    ap.add_argument("--inducing", dest="m", type=int, default=128)
+    ap.add_argument("--dim", dest="d", type=int, default=4)
+    ap.add_argument("--particles", dest="j", type=int, default=512)
     ap.add_argument("--steps", type=int, default=3)
     args = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
