@@ -174,6 +174,13 @@ int pls_project_update_f64(pls_ctx* ctx, const double* vt, int64_t ldv, int64_t 
                            int noise_mode, const double* xi, int64_t ldxi, uint64_t seed, uint64_t step,
                            int64_t j_global_offset, int in_place, double* out, int64_t ldo, void* stream);
 
+/* CUDA-graph support for the Philox stream: a captured pls_project_update_f64 freezes its `step` argument, so a replayed
+ * graph would repeat its noise.  With a counter installed, the step index the kernel uses is `step + *counter_dev` (read on
+ * the device at run time); pls_advance_step_counter enqueues `*counter_dev += increment` and is captured with the step.
+ * pls_set_step_counter(ctx, NULL) restores the plain behaviour. */
+void pls_set_step_counter(pls_ctx* ctx, const uint64_t* counter_dev);
+int pls_advance_step_counter(pls_ctx* ctx, uint64_t* counter_dev, uint64_t increment, void* stream);
+
 /* Elementwise d_2 c(y, F) on a caller-provided F (n x j): <Cost>.calculate_cost_derivative, pls/costs/*.py. */
 int pls_cost_derivative_f64(pls_ctx* ctx, const pls_cost* cost, const double* y, const double* f, int64_t ldf,
                             int64_t n, int64_t j, double* out, int64_t ldo, void* stream);

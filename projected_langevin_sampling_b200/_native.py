@@ -75,6 +75,8 @@ SIGNATURES = {
         _int,
         [_vp, _vp, _i64, _i64, _i64, _vp, _i64, _vp, _i64, _i64, _vp, _dbl, _int, _vp, _i64, _u64, _u64, _i64, _int, _vp, _i64, _vp],
     ),
+    "pls_set_step_counter": (None, [_vp, _vp]),
+    "pls_advance_step_counter": (_int, [_vp, _vp, _u64, _vp]),
     "pls_cost_derivative_f64": (_int, [_vp, _costp, _vp, _vp, _i64, _i64, _i64, _vp, _i64, _vp]),
     "pls_cost_value_f64": (_int, [_vp, _costp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp]),
     "pls_energy_terms_f64": (_int, [_vp, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _vp, _vp]),

@@ -84,23 +84,26 @@ int pls_point_stride(int d) {
 }
 
 int pls_backward_splits(const pls_ctx* ctx, int64_t n_rows, int64_t m, int64_t j) {
-  // Enough CTAs for >= 8 waves of one CTA per SM, a whole number of waves when possible, and splits no shorter than
-  // 16 pipeline chunks.
+  // Enough CTAs for >= 8 waves of one CTA per SM when the reduction is long enough (splits no shorter than 8 pipeline
+  // stages), and among the admissible counts the one that fills whole waves best (ties: fewer splits, less Gp traffic).
   const int sms = (ctx && ctx->sm_count > 0) ? ctx->sm_count : 148;
   const int rt = pls::choose_tile_rt(ctx, j);
   const int64_t br = pls::tile_rows(rt), bj = pls::tile_cols(rt);
   const int64_t tiles = ((m + br - 1) / br) * ((j + bj - 1) / bj);
   if (tiles <= 0 || n_rows <= 0) return 1;
   const int64_t chunks = (n_rows + pls::BK - 1) / pls::BK;
-  int64_t max_splits = chunks / 16;
+  int64_t max_splits = chunks / 8;
   if (max_splits < 1) max_splits = 1;
+  if (max_splits > 4096) max_splits = 4096;
   int64_t want = (8LL * sms + tiles - 1) / tiles;
   if (want < 1) want = 1;
-  if (want > max_splits) want = max_splits;
-  // look a little further for a split count that fills whole waves
-  int64_t best = want;
+  int64_t hi = want + 64, lo = want;
+  if (hi > max_splits) hi = max_splits;
+  if (lo > hi) lo = (hi + 1) / 2;  // short reduction: trade split length for a full wave
+  if (lo < 1) lo = 1;
+  int64_t best = lo;
   double best_eff = 0.0;
-  for (int64_t s = want; s <= want + 64 && s <= max_splits; ++s) {
+  for (int64_t s = lo; s <= hi; ++s) {
     const int64_t ctas = tiles * s;
     const int64_t waves = (ctas + sms - 1) / sms;
     const double eff = (double)ctas / (double)(waves * sms);
@@ -109,7 +112,6 @@ int pls_backward_splits(const pls_ctx* ctx, int64_t n_rows, int64_t m, int64_t j
       best = s;
     }
   }
-  if (best > 4096) best = 4096;
   return (int)best;
 }
 
@@ -235,7 +237,18 @@ int pls_project_update_f64(pls_ctx* ctx, const double* vt, int64_t ldv, int64_t 
   p.a = vt; p.lda = ldv; p.b = gm; p.ldb = ldg; p.c = out; p.ldc = ldo; p.rows = m_k; p.j = j; p.k = m;
   p.particles = p_; p.ldp = ldp; p.inv_lambda = inv_lambda; p.xi = xi; p.ldxi = ldxi; p.eta = eta;
   p.noise_mode = noise_mode; p.in_place = in_place; p.seed = seed; p.step = step; p.j_global_offset = j_global_offset;
+  p.step_counter = ctx->step_counter;
   return check_cuda(ctx, pls::launch_small_gemm(p, true, true, (cudaStream_t)stream), "pls_project_update_f64");
+}
+
+void pls_set_step_counter(pls_ctx* ctx, const uint64_t* counter_dev) {
+  if (ctx) ctx->step_counter = counter_dev;
+}
+
+int pls_advance_step_counter(pls_ctx* ctx, uint64_t* counter_dev, uint64_t increment, void* stream) {
+  if (!ctx) return 1;
+  if (!counter_dev) return fail(ctx, "pls_advance_step_counter: NULL counter");
+  return check_cuda(ctx, pls::launch_advance_counter(counter_dev, increment, (cudaStream_t)stream), "pls_advance_step_counter");
 }
 
 int pls_cost_derivative_f64(pls_ctx* ctx, const pls_cost* cost, const double* y, const double* f, int64_t ldf, int64_t n,

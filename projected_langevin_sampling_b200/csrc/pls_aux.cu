@@ -193,6 +193,7 @@ __global__ void __launch_bounds__(128) small_gemm_kernel(const SmallGemmParams p
 
   const double sq2eta = sqrt(2.0 * p.eta);
 #pragma unroll
+  const uint64_t step = (UPDATE && p.step_counter) ? p.step + *p.step_counter : p.step;
   for (int mt = 0; mt < 4; ++mt) {
     const int64_t r = row0 + wm * 32 + mt * 8 + g;
     if (r >= p.rows) continue;
@@ -208,7 +209,7 @@ __global__ void __launch_bounds__(128) small_gemm_kernel(const SmallGemmParams p
           const double pv = p.particles[r * p.ldp + c];
           double xi = 0.0;
           if (p.noise_mode == PLS_NOISE_GIVEN) xi = p.xi[r * p.ldxi + c];
-          else if (p.noise_mode == PLS_NOISE_PHILOX) xi = philox_normal(p.seed, p.step, r, p.j_global_offset + c);
+          else if (p.noise_mode == PLS_NOISE_PHILOX) xi = philox_normal(p.seed, step, r, p.j_global_offset + c);
           double delta = -p.eta * v - p.eta * (p.inv_lambda[r] * pv);
           delta = delta + sq2eta * xi;
           v = p.in_place ? (pv + delta) : delta;
@@ -217,6 +218,13 @@ __global__ void __launch_bounds__(128) small_gemm_kernel(const SmallGemmParams p
       }
     }
   }
+}
+
+__global__ void advance_counter_kernel(uint64_t* counter, uint64_t increment) { *counter += increment; }
+
+cudaError_t launch_advance_counter(uint64_t* counter, uint64_t increment, cudaStream_t stream) {
+  advance_counter_kernel<<<1, 1, 0, stream>>>(counter, increment);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_small_gemm(const SmallGemmParams& p, bool trans_a, bool update, cudaStream_t stream) {

@@ -28,6 +28,7 @@ struct SmallGemmParams {
   int noise_mode;
   int in_place;
   uint64_t seed, step;
+  const uint64_t* step_counter;  // optional device counter added to `step` (CUDA-graph replay: the host value is frozen)
   int64_t j_global_offset;
 };
 
@@ -47,6 +48,7 @@ cudaError_t launch_cost_value(const pls_cost& cost, const double* y, const doubl
 cudaError_t launch_energy_terms(const double* partial, int64_t tiles, int64_t ldpart, const double* p, int64_t ldp,
                                 int64_t m_k, const double* inv_lambda, int64_t j, double* out, cudaStream_t stream);
 
+cudaError_t launch_advance_counter(uint64_t* counter, uint64_t increment, cudaStream_t stream);
 cudaError_t launch_gram_exp(const double* x, int64_t n, int fast, double* out, cudaStream_t stream);
 
 // ConditionalVariance selector (pls_selector.cu)

@@ -13,6 +13,7 @@ struct pls_ctx {
   int device = 0;
   int sm_count = 0;
   int max_smem_optin = 0;
+  const uint64_t* step_counter = nullptr;  // device counter added to pls_project_update_f64's `step` (pls_set_step_counter)
   int tile_rt = 0;  // 0 = choose per launch from the particle count; 1 / 2 force a tile shape (PLS_B200_TILE_RT, tests)
   std::string error;
 };

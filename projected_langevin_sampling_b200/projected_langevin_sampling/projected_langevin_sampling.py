@@ -78,14 +78,51 @@ class PLS:
         return self.basis.calculate_energy_potential(particles=particles, cost=cost)
 
     def run(self, particles: torch.Tensor, step_size: float, number_of_steps: int, seed: Optional[int] = None,
-            j_global_offset: int = 0, energy_every: int = 0) -> Tuple[torch.Tensor, List[float]]:
+            j_global_offset: int = 0, energy_every: int = 0, cuda_graph: bool = False) -> Tuple[torch.Tensor, List[float]]:
         """The caller's loop (experiments/trainers.py:149-161) run in place on the device.  With `seed` the noise is the
-        Philox stream keyed on (seed, step, row, global particle); without it the reference's host stream is replayed."""
+        Philox stream keyed on (seed, step, row, global particle); without it the reference's host stream is replayed.
+        cuda_graph=True (Philox noise only) captures ONE step -- its five kernel launches plus the increment of a device
+        step counter -- in a CUDA graph and replays it: for small problems (BASELINE configs 1-3) a step is tens of
+        microseconds of GPU work and the eager loop is bound by launch + host overhead.  The particles are the same."""
         energies: List[float] = []
+        if cuda_graph:
+            if seed is None:
+                raise ValueError("cuda_graph=True needs the device-side Philox noise (seed=...): the reference's host noise "
+                                 "stream cannot be captured")
+            return self._run_graph(particles, step_size, number_of_steps, seed, j_global_offset, energy_every)
         for s in range(number_of_steps):
             self.step_(particles, step_size, philox=None if seed is None else (seed, s, j_global_offset))
             if energy_every and (s + 1) % energy_every == 0:
                 energies.append(self.calculate_energy_potential(particles))
+        return particles, energies
+
+    def _run_graph(self, particles: torch.Tensor, step_size: float, number_of_steps: int, seed: int, j_global_offset: int,
+                   energy_every: int) -> Tuple[torch.Tensor, List[float]]:
+        from .. import _native as nat
+
+        ctx = nat.context(particles.device)
+        energies: List[float] = []
+        if number_of_steps <= 0:
+            return particles, energies
+        self.basis.engine(particles.shape[1])  # workspaces must exist before capture
+        counter = torch.zeros(1, dtype=torch.int64, device=particles.device)
+        # warm-up on a scratch copy: first-launch work (function attributes, lazy module loading) must not happen in capture
+        self.step_(particles.clone(), step_size, philox=(seed, 0, j_global_offset))
+        torch.cuda.synchronize(particles.device)
+        graph = torch.cuda.CUDAGraph()
+        ctx.lib.pls_set_step_counter(ctx.handle, counter.data_ptr())
+        try:
+            with torch.cuda.graph(graph):
+                self.step_(particles, step_size, philox=(seed, 0, j_global_offset))  # step index = 0 + *counter
+                ctx.check(ctx.lib.pls_advance_step_counter(ctx.handle, counter.data_ptr(), 1, ctx.stream()))
+        finally:
+            ctx.lib.pls_set_step_counter(ctx.handle, None)
+        # capture does not execute: `particles` and the counter are untouched so far
+        for s in range(number_of_steps):
+            graph.replay()
+            if energy_every and (s + 1) % energy_every == 0:
+                energies.append(self.calculate_energy_potential(particles))
+        torch.cuda.synchronize(particles.device)
         return particles, energies
 
     # ---- prediction (:140-204) -------------------------------------------------------------------------------------------

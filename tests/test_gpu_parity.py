@@ -575,3 +575,19 @@ def test_train_pls_matches_stepwise_api(b200):
         assert rel_err(p, p_ref) < 1e-11
     finally:
         torch.set_default_dtype(torch.float32)
+
+
+def test_cuda_graph_run_equals_eager_run(b200):
+    """PLS.run(cuda_graph=True): one captured step replayed with a device-side Philox step counter gives exactly the eager
+    loop's particles (same kernels, same arguments), at a launch-bound size."""
+    x, y, z, ls, g = _problem(2000, 1, 32, 256, seed=12, cost_kind="bernoulli")
+    pls, _ = _build_pair(b200, x, y, z, ls, 1.0, "bernoulli", "sigmoid")
+    p0 = torch.randn(pls.basis.approximation_dimension, 256, generator=g, dtype=torch.float64).cuda()
+    eager, _ = pls.run(p0.clone(), 1e-3, 25, seed=5, j_global_offset=64)
+    graphed, energies = pls.run(p0.clone(), 1e-3, 25, seed=5, j_global_offset=64, cuda_graph=True, energy_every=10)
+    assert torch.equal(eager, graphed)
+    assert len(energies) == 2 and all(np.isfinite(energies))
+    again, _ = pls.run(p0.clone(), 1e-3, 25, seed=5, j_global_offset=64)  # the counter hook is uninstalled afterwards
+    assert torch.equal(eager, again)
+    with pytest.raises(ValueError):
+        pls.run(p0.clone(), 1e-3, 2, cuda_graph=True)
