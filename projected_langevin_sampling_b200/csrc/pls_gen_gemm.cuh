@@ -237,23 +237,40 @@ __global__ void __launch_bounds__(NTHREADS, 1)
   const int off0 = (2 * t) * 128 + ((g ^ (2 * t)) << 4);
   const int off1 = (2 * t + 1) * 128 + ((g ^ (2 * t + 1)) << 4);
 
-  double s[RT][2];  // exponents of the group in flight
-  double k0[RT];    // Gram values of k4 step 0 (point 2t)
+  // Gram values are generated one BLOCK of LA groups ahead of the DMMAs that consume them: the 2 RT LA exponent chains of a
+  // block are independent, so they issue back to back at the pipe's rate instead of stalling the (in-order) warp on each
+  // dependent FP64 op, and ptxas is free to spread them over the block's DMMAs.  LA = 4 (a whole stage) for RT = 1; 2 for
+  // RT = 2 (register budget).
+  constexpr int GROUPS = BK / 8;
+  constexpr int LA = (RT == 1) ? GROUPS : GROUPS / 2;
+  constexpr int NBLK = GROUPS / LA;
+  // Gram values of groups [g0, g0 + LA) of the point tile Pt; `first` = this thread's first reduction point of group g0,
+  // counted from `begin` (points past the end of the reduction give 0)
+  auto gram_block = [&](const double* Pt, int g0, int first, double (&k)[LA][2][RT]) {
 #pragma unroll
-  for (int h = 0; h < RT; ++h) k0[h] = 0.0;
+    for (int q = 0; q < LA; ++q) {
+      double s[RT][2];
+      exponent_tile(Pt, g0 + q, s);
+#pragma unroll
+      for (int h = 0; h < RT; ++h) {
+        k[q][0][h] = gram_value(s[h][0], first + 8 * q < red_len);
+        k[q][1][h] = gram_value(s[h][1], first + 8 * q + 1 < red_len);
+      }
+    }
+  };
+
+  double kc[LA][2][RT];  // Gram values of the block being multiplied
   if (nchunks > 0) {
     mbar_wait(&full[0], 0u);
-    exponent_tile(sP, 0, s);
-#pragma unroll
-    for (int h = 0; h < RT; ++h) k0[h] = gram_value(s[h][0], 2 * t < red_len);
+    gram_block(sP, 0, 2 * t, kc);
   }
   int stage = 0;
   uint32_t phase = 0;  // of the chunk being consumed
 #pragma unroll 1
   for (int c = 0; c < nchunks; ++c) {
     // One iteration = one 32-point stage = 4 groups, fully unrolled into a single basic block (264 DMMAs).  The next stage
-    // must have landed before the last group forms the exponents of the next chunk's first group; it was issued two chunk
-    // times ago, so waiting for it here, once per chunk, costs nothing.
+    // must have landed before its Gram values are formed; it was issued two chunk times ago, so waiting for it here, once
+    // per chunk, costs nothing.
     const int nstage = (stage + 1 == STAGES) ? 0 : stage + 1;
     const uint32_t nphase = (nstage == 0) ? (phase ^ 1u) : phase;
     if (c + 1 < nchunks) mbar_wait(&full[nstage], nphase);
@@ -262,19 +279,23 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     const double* Pn = sP + nstage * BK * sp;
     const int base = c * BK + 2 * t;  // this thread's first reduction point of the chunk, counted from `begin`
 #pragma unroll
-    for (int grp = 0; grp < BK / 8; ++grp) {
-      const int pg = base + 8 * grp;  // this thread's two reduction points: pg (k4 step 0) and pg + 1 (k4 step 1)
-      // k4 step 0 with k0; meanwhile the Gram values of step 1
-      double k1[RT];
+    for (int blk = 0; blk < NBLK; ++blk) {
+      double kn[LA][2][RT];  // the next block (of this chunk, or the first of the next chunk; past the end: masked)
+      if (blk + 1 < NBLK) gram_block(Pt, (blk + 1) * LA, base + 8 * (blk + 1) * LA, kn);
+      else gram_block(Pn, 0, base + BK, kn);
 #pragma unroll
-      for (int h = 0; h < RT; ++h) k1[h] = gram_value(s[h][1], pg + 1 < red_len);
-      mma_step(bchunk + grp * 1024 + off0, k0);
-      // k4 step 1 with k1; meanwhile exponents + step-0 Gram values of the next group (past the end: masked)
-      if (grp + 1 < BK / 8) exponent_tile(Pt, grp + 1, s);
-      else exponent_tile(Pn, 0, s);
+      for (int q = 0; q < LA; ++q) {
+        const unsigned char* bgrp = bchunk + (blk * LA + q) * 1024;
+        mma_step(bgrp + off0, kc[q][0]);
+        mma_step(bgrp + off1, kc[q][1]);
+      }
 #pragma unroll
-      for (int h = 0; h < RT; ++h) k0[h] = gram_value(s[h][0], pg + 8 < red_len);
-      mma_step(bchunk + grp * 1024 + off1, k1);
+      for (int q = 0; q < LA; ++q)
+#pragma unroll
+        for (int h = 0; h < RT; ++h) {
+          kc[q][0][h] = kn[q][0][h];
+          kc[q][1][h] = kn[q][1][h];
+        }
     }
     if (c + STAGES < nchunks) {  // chunk c fully consumed by this warp and its stage is needed again
       __syncwarp();
