@@ -52,6 +52,7 @@ class OrthonormalBasis(PLSBasis):
         # augmented point sets, centred on the inducing points' mean (orthonormal.py:36-41: the two kernel calls)
         centre = self.x_induce.mean(dim=0).tolist() if self._spec.kernel_id == nat.KERNEL_RBF else [0.0] * d
         inv_ls = self._spec.inv_lengthscale
+        self._centre = centre
         self._za = ops.prepare_points(self.ctx, self._spec.kernel_id, self.x_induce, inv_ls, centre, self._spec.log_outputscale)
         za_plain = ops.prepare_points(self.ctx, self._spec.kernel_id, self.x_induce, inv_ls, centre, 0.0)
         self._xa = ops.prepare_points(self.ctx, self._spec.kernel_id, self._x_train, inv_ls, centre, 0.0)
@@ -191,11 +192,18 @@ class OrthonormalBasis(PLSBasis):
         return predictive_noise
 
     def predict_untransformed_samples(self, particles: torch.Tensor, x: torch.Tensor, noise: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """noise[M_k:] + k(x, Z) V~ (P - noise[:M_k])  (orthonormal.py:216-244).  The contraction runs through the same
+        generated-operand kernel as the training forward (pls_gemm_f64 + pls_forward_f64): k(x, Z) is not materialised."""
         p = self._particles(particles)
         x = ops.as_device_f64(x if x.dim() > 1 else x.unsqueeze(-1), p.device)
-        base_gram_x_induce = dense_gram(self.kernel.base_kernel, x, self.x_induce)
         if noise is None:
             noise = self.sample_predictive_noise(particles=p, x=x)
         noise = ops.as_device_f64(noise, p.device)
         m_k = self.approximation_dimension
-        return noise[m_k:, :] + (base_gram_x_induce @ self.scaled_eigenvectors @ (p - noise[:m_k, :]))
+        j = p.shape[1]
+        xa = ops.prepare_points(self.ctx, self._spec.kernel_id, x, self._spec.inv_lengthscale, self._centre, 0.0)
+        w, _ = ops.alloc_matrix(self.x_induce.shape[0], j, p.device)
+        ops.gemm(self.ctx, self.scaled_eigenvectors, (p - noise[:m_k, :]).contiguous(), w)  # W = V~ (P - noise_top)
+        out, _ = ops.alloc_matrix(x.shape[0], j, p.device)
+        ops.forward(self.ctx, self._spec.kernel_id, xa, self._za, self._d, w, j, nat.EPI_PREDICTION, out)
+        return noise[m_k:, :] + out[:, :j]

@@ -591,3 +591,16 @@ def test_cuda_graph_run_equals_eager_run(b200):
     assert torch.equal(eager, again)
     with pytest.raises(ValueError):
         pls.run(p0.clone(), 1e-3, 2, cuda_graph=True)
+
+
+def test_predict_untransformed_samples_matches_oracle(b200):
+    """Prediction at new inputs with the predictive noise given (orthonormal.py:216-244): RBF/ARD kernel, ragged sizes."""
+    x, y, z, ls, g = _problem(900, 4, 50, 33, seed=14)
+    pls, orc = _build_pair(b200, x, y, z, ls, 1.3, "gaussian", "identity")
+    m_k = orc.basis.approximation_dimension
+    xs = torch.randn(257, 4, generator=g, dtype=torch.float64)
+    p = torch.randn(m_k, 33, generator=g, dtype=torch.float64)
+    noise = 0.1 * torch.randn(m_k + 257, 33, generator=g, dtype=torch.float64)
+    want = orc.basis.predict_untransformed_samples(p, xs, noise=noise)
+    got = pls.predict_untransformed_samples(p.cuda(), xs, noise=noise)
+    assert rel_err(got, want) < TOL
