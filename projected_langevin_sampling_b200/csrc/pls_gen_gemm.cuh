@@ -41,6 +41,22 @@ namespace {
 constexpr int NWARPS = NTHREADS / 32;
 constexpr int BLOCK_BYTES = BK * 128;  // one 16-column block of a stage: 32 rows x 128 bytes
 
+// Four cost derivatives per call (one accumulator column group), arguments and results in registers.  Called, not inlined,
+// from the register epilogue: 16 calls per thread and tile keep the kernel small while the four evaluations inside give
+// the transcendental functors instruction-level parallelism.  `c` points to a shared-memory copy of the cost.
+struct D4 {
+  double a, b, c, d;
+};
+static __device__ __noinline__ D4 cost_derivative4(const pls_cost* c, double y, D4 f) {
+  const pls_cost cc = *c;
+  D4 r;
+  r.a = cost_derivative(cc, y, f.a);
+  r.b = cost_derivative(cc, y, f.b);
+  r.c = cost_derivative(cc, y, f.c);
+  r.d = cost_derivative(cc, y, f.d);
+  return r;
+}
+
 template <int RT>
 struct Tile {
   static constexpr int NT = 32 / RT;          // n8 column tiles per warp
@@ -51,14 +67,15 @@ struct Tile {
   static constexpr int SF = BJ + 2;           // row stride (doubles) of the forward epilogue's staging tile
 };
 
-constexpr int SMEM_HEADER = 2048;  // barriers + counters + exp table [0, 1024) | y of the tile's rows [1024, 2048)
+constexpr int SMEM_HEADER = 4096;  // barriers + counters + exp table [0, 1024) | y of the rows of two tiles [1024, 3072)
 
 // shared memory: header | STAGES x stage (1024-aligned) | STAGES x BK x sp points
 template <int RT>
 __host__ __device__ inline size_t gen_gemm_smem_bytes(int sp) {
+  // the forward epilogue stages the output tile through ONE pipeline stage (32 rows at a time): no extra staging memory
   const size_t pipeline = (size_t)STAGES * Tile<RT>::STAGE_BYTES + sizeof(double) * (size_t)(STAGES * BK * sp);
-  const size_t staging = sizeof(double) * (size_t)(Tile<RT>::BR * Tile<RT>::SF + 2 * NTHREADS);  // + cost scratch
-  return 1024 /* alignment slack */ + SMEM_HEADER + (pipeline > staging ? pipeline : staging);
+  const size_t cost_scratch = sizeof(double) * 2 * NTHREADS;  // [PHASES][BJ]
+  return 1024 /* alignment slack */ + SMEM_HEADER + pipeline + cost_scratch;
 }
 
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar) {
@@ -86,15 +103,17 @@ template <int NKD, bool BACKWARD, bool RBF, int RT>
 __global__ void __launch_bounds__(NTHREADS, 1)
     gen_gemm_kernel(const GenGemmParams p, const __grid_constant__ CUtensorMap tm3, const __grid_constant__ CUtensorMap tm2) {
   using T = Tile<RT>;
-  constexpr int NT = T::NT, BR = T::BR, BJ = T::BJ, NPR = T::NPR, STAGE_BYTES = T::STAGE_BYTES, SF = T::SF;
+  constexpr int NT = T::NT, BR = T::BR, BJ = T::BJ, NPR = T::NPR, STAGE_BYTES = T::STAGE_BYTES;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);  // the swizzle needs 1024-byte stages
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);                      // [STAGES]
   unsigned* released = reinterpret_cast<unsigned*>(smem_raw + 64);             // [STAGES] warps done with the stage
   double* sExp = reinterpret_cast<double*>(smem_raw + 128);                    // 2^(j/64)
-  double* sY = reinterpret_cast<double*>(smem_raw + 1024);                     // [BR] targets of the tile's rows (forward)
+  pls_cost* sCost = reinterpret_cast<pls_cost*>(smem_raw + 704);              // the cost, for the called functor
+  double* sYall = reinterpret_cast<double*>(smem_raw + 1024);                  // [2][128] targets of the tile's rows (forward)
   unsigned char* sB = smem_raw + SMEM_HEADER;                                  // [STAGES][NPR][BK rows][128 bytes], swizzled
   double* sP = reinterpret_cast<double*>(sB + STAGES * STAGE_BYTES);           // [STAGES][BK][sp]
+  double* sC = sP + STAGES * BK * p.sp;                                        // [PHASES][BJ] cost-sum scratch (forward)
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -103,26 +122,27 @@ __global__ void __launch_bounds__(NTHREADS, 1)
   const int t = lane & 3;   // DMMA thread-in-group
   const int sp = p.sp;
 
-  // ---- which tile / which slice of the reduction ---------------------------------------------------------------
+  // ---- tiles of this CTA ------------------------------------------------------------------------------------------------
+  // backward role: ONE tile = (inducing-row tile, column tile, split of the training rows), row tiles fastest so that the CTAs
+  //   streaming the same Dc slab run together and share it in L2;
+  // forward role: PERSISTENT -- the grid is one CTA per SM and CTA b takes tiles b, b + grid, b + 2 grid, ... (column tiles
+  //   fastest: the CTAs in flight share training rows and the whole W).  The copy pipeline runs across tile boundaries (the
+  //   first stages of the next tile land during the epilogue of the current one) and nothing is re-initialised per tile.
   const int64_t n_row_tiles = (p.n_rows + BR - 1) / BR;
   const int64_t n_col_tiles = (p.j + BJ - 1) / BJ;
-  int64_t bid = blockIdx.x;
-  int64_t rt, ct;
-  int split = 0;
-  if (!BACKWARD) {  // particles fastest: neighbouring CTAs share the same training rows
-    ct = bid % n_col_tiles;
-    rt = bid / n_col_tiles;
-  } else {  // inducing-row tiles fastest: the CTAs that stream the same Dc slab run together and share it in L2
-    rt = bid % n_row_tiles;
-    bid /= n_row_tiles;
-    ct = bid % n_col_tiles;
-    split = (int)(bid / n_col_tiles);
-  }
-  const int64_t row0 = rt * BR;
-  const int64_t j0 = ct * BJ;
+  const int64_t total_tiles = n_row_tiles * n_col_tiles * (BACKWARD ? p.splits : 1);
+  const int my_tiles = BACKWARD ? 1 : (int)((total_tiles - (int64_t)blockIdx.x + gridDim.x - 1) / gridDim.x);
 
+  // reduction range: the forward role reduces over all inducing points in every tile; the backward role over its split
   int64_t begin = 0, end = p.red_total;
+  int64_t bw_rt = 0, bw_ct = 0;
+  int split = 0;
   if (BACKWARD) {
+    int64_t bid = blockIdx.x;
+    bw_rt = bid % n_row_tiles;
+    bid /= n_row_tiles;
+    bw_ct = bid % n_col_tiles;
+    split = (int)(bid / n_col_tiles);
     const int64_t total_chunks = (p.red_total + BK - 1) / BK;
     const int64_t per = (total_chunks + p.splits - 1) / p.splits;
     begin = (int64_t)split * per * BK;
@@ -131,14 +151,25 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     if (begin > end) begin = end;
   }
   const int red_len = (int)(end - begin);
-  const int nchunks = (red_len + BK - 1) / BK;
+  const int nchunks = (red_len + BK - 1) / BK;         // per tile
+  const int total_gc = my_tiles * nchunks;             // chunks this CTA streams, over all its tiles (the launcher checks the range)
+  auto tile_coords = [&](int ti, int64_t& rt, int64_t& ct) {
+    if (BACKWARD) {
+      rt = bw_rt;
+      ct = bw_ct;
+    } else {
+      const int64_t tile = (int64_t)blockIdx.x + (int64_t)ti * gridDim.x;
+      ct = tile % n_col_tiles;
+      rt = tile / n_col_tiles;
+    }
+  };
 
   // ---- one-time setup -------------------------------------------------------------------------------------------
   // point rows past the end of the reduction are never copied: keep them finite
   for (int i = tid; i < STAGES * BK * sp; i += NTHREADS) sP[i] = 0.0;
   if (tid < 64) sExp[tid] = kExp2Table[tid];
-  if (!BACKWARD && p.epilogue != PLS_EPI_PREDICTION && tid < BR) sY[tid] = (row0 + tid < p.n_rows) ? p.y[row0 + tid] : 0.0;
   if (tid == 0) {
+    *sCost = p.cost;
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
       released[s] = 0;
@@ -150,10 +181,15 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 
   // One thread fills a stage: one tensor-map copy for the streamed tile (all BJ/16 column blocks; rows or columns outside
   // the matrix arrive as zeros), one bulk copy for the reduction-point rows.  The 3-D map cannot describe a partial last
-  // column block, so a tile that contains one uses the 2-D map block by block.
-  const bool use3d = p.tma3d && (j0 + BJ <= p.full_blocks * 16 || p.full_blocks * 16 == p.ldb);
-  auto issue = [&](int c) {
-    const int stage = c % STAGES;
+  // column block, so a tile that contains one uses the 2-D map block by block.  gc = chunk index over all tiles of the CTA.
+  auto issue = [&](int gc) {
+    const int ti = gc / nchunks;
+    const int c = gc - ti * nchunks;
+    int64_t rt, ct;
+    tile_coords(ti, rt, ct);
+    const int64_t j0 = ct * BJ;
+    const bool use3d = p.tma3d && (j0 + BJ <= p.full_blocks * 16 || p.full_blocks * 16 == p.ldb);
+    const int stage = gc % STAGES;
     const int64_t k0 = begin + (int64_t)c * BK;
     const int kc = (int)((end - k0 < BK) ? (end - k0) : BK);
     uint64_t* bar = &full[stage];
@@ -168,38 +204,29 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     bulk_g2s(sP + stage * BK * sp, p.red_aug + k0 * sp, (uint32_t)(kc * sp * 8), bar);
   };
   if (tid == 0) {
-    for (int c = 0; c < STAGES && c < nchunks; ++c) issue(c);
+    for (int gc = 0; gc < STAGES && gc < total_gc; ++gc) issue(gc);
   }
 
   // row-side exponent fragments (A operand of the S DMMA): row g of each of this warp's RT row tiles.  Coordinates only;
   // the c entry (column d of the augmented row) seeds the accumulator together with the point's c.
   double a2[RT][NKD];
   double crow[RT];
+  auto load_rows = [&](int64_t row0, double (&a)[RT][NKD], double (&cr)[RT]) {
 #pragma unroll
-  for (int h = 0; h < RT; ++h) {
-    const int64_t r = row0 + (warp * RT + h) * 8 + g;
-    const bool rv = r < p.n_rows;
+    for (int h = 0; h < RT; ++h) {
+      const int64_t r = row0 + (warp * RT + h) * 8 + g;
+      const bool rv = r < p.n_rows;
 #pragma unroll
-    for (int kd = 0; kd < NKD; ++kd) {
-      const int dd = t + 4 * kd;
-      a2[h][kd] = (rv && dd < p.d) ? p.rows_aug[r * sp + dd] : 0.0;
+      for (int kd = 0; kd < NKD; ++kd) {
+        const int dd = t + 4 * kd;
+        a[h][kd] = (rv && dd < p.d) ? p.rows_aug[r * sp + dd] : 0.0;
+      }
+      cr[h] = rv ? p.rows_aug[r * sp + p.d] : 0.0;
     }
-    crow[h] = rv ? p.rows_aug[r * sp + p.d] : 0.0;
-  }
+  };
 
   double acc[RT][NT][2];
-#pragma unroll
-  for (int h = 0; h < RT; ++h)
-#pragma unroll
-    for (int nt = 0; nt < NT; ++nt) {
-      acc[h][nt][0] = 0.0;
-      acc[h][nt][1] = 0.0;
-    }
 
-  // ---- main loop over groups of 8 reduction points ------------------------------------------------------------------
-  // Software-pipelined at k4-step granularity: while the DMMAs of one k4 step (one reduction point per thread) are
-  // issued, the Gram values of the NEXT k4 step are generated (S DMMAs + exp), so the latency of the exponent chain
-  // hides behind this warp's own tensor work.
   // exponents of group `grp` of the point tile Pt: S[h] (8 rows x 8 points) in C-fragment layout
   auto exponent_tile = [&](const double* Pt, int grp, double (&s)[RT][2]) {
     const double* prow = Pt + (grp * 8 + g) * sp;          // B fragment: point g of the group, coordinate t + 4 kd
@@ -239,8 +266,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 
   // Gram values are generated one BLOCK of LA groups ahead of the DMMAs that consume them: the 2 RT LA exponent chains of a
   // block are independent, so they issue back to back at the pipe's rate instead of stalling the (in-order) warp on each
-  // dependent FP64 op, and ptxas is free to spread them over the block's DMMAs.  LA = 4 (a whole stage) for RT = 1; 2 for
-  // RT = 2 (register budget).
+  // dependent FP64 op.  LA = 4 (a whole stage) for RT = 1; 2 for RT = 2 (register budget).
   constexpr int GROUPS = BK / 8;
   constexpr int LA = (RT == 1) ? GROUPS : GROUPS / 2;
   constexpr int NBLK = GROUPS / LA;
@@ -259,157 +285,265 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     }
   };
 
-  double kc[LA][2][RT];  // Gram values of the block being multiplied
-  if (nchunks > 0) {
-    mbar_wait(&full[0], 0u);
-    gram_block(sP, 0, 2 * t, kc);
-  }
+  // Forward epilogues.  PREDICTION and COST_DERIVATIVE are written straight from the accumulator registers with 256-bit
+  // stores: no shared-memory staging and NO block-wide synchronisation, so the warps of the persistent CTA drift apart and
+  // one warp's epilogue overlaps the others' tensor work.  The Gaussian / identity closed form (one multiply-subtract per
+  // element) is inline, every other cost functor is called four values at a time.  The epilogues that produce cost sums
+  // need the tile's rows together and are staged through shared memory.
+  const bool deriv_direct = !BACKWARD && p.epilogue == PLS_EPI_COST_DERIVATIVE;
+  const bool gauss_direct = deriv_direct && p.cost.cost_id == PLS_COST_GAUSSIAN && p.cost.link_id == PLS_LINK_IDENTITY &&
+                            p.cost.closed_form != 0;
+  const bool direct = !BACKWARD && (p.epilogue == PLS_EPI_PREDICTION || deriv_direct);
+  const double inv_noise = gauss_direct ? (1.0 / p.cost.observation_noise) : 1.0;  // as cost_derivative(): gaussian.py:75-88
+  const bool wide_store = ((p.ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 31u) == 0);
+
   int stage = 0;
-  uint32_t phase = 0;  // of the chunk being consumed
-#pragma unroll 1
-  for (int c = 0; c < nchunks; ++c) {
-    // One iteration = one 32-point stage = 4 groups, fully unrolled into a single basic block (264 DMMAs).  The next stage
-    // must have landed before its Gram values are formed; it was issued two chunk times ago, so waiting for it here, once
-    // per chunk, costs nothing.
-    const int nstage = (stage + 1 == STAGES) ? 0 : stage + 1;
-    const uint32_t nphase = (nstage == 0) ? (phase ^ 1u) : phase;
-    if (c + 1 < nchunks) mbar_wait(&full[nstage], nphase);
-    const unsigned char* bchunk = sB + stage * STAGE_BYTES;
-    const double* Pt = sP + stage * BK * sp;
-    const double* Pn = sP + nstage * BK * sp;
-    const int base = c * BK + 2 * t;  // this thread's first reduction point of the chunk, counted from `begin`
-#pragma unroll
-    for (int blk = 0; blk < NBLK; ++blk) {
-      double kn[LA][2][RT];  // the next block (of this chunk, or the first of the next chunk; past the end: masked)
-      if (blk + 1 < NBLK) gram_block(Pt, (blk + 1) * LA, base + 8 * (blk + 1) * LA, kn);
-      else gram_block(Pn, 0, base + BK, kn);
-#pragma unroll
-      for (int q = 0; q < LA; ++q) {
-        const unsigned char* bgrp = bchunk + (blk * LA + q) * 1024;
-        mma_step(bgrp + off0, kc[q][0]);
-        mma_step(bgrp + off1, kc[q][1]);
-      }
-#pragma unroll
-      for (int q = 0; q < LA; ++q)
-#pragma unroll
-        for (int h = 0; h < RT; ++h) {
-          kc[q][0][h] = kn[q][0][h];
-          kc[q][1][h] = kn[q][1][h];
-        }
-    }
-    if (c + STAGES < nchunks) {  // chunk c fully consumed by this warp and its stage is needed again
-      __syncwarp();
-      if (lane == 0) {
-        // the last warp to release the stage refills it: nobody waits
-        if (atom_add_shared(&released[stage], 1u) == NWARPS - 1) {
-          released[stage] = 0;
-          issue(c + STAGES);
-        }
-      }
-    }
-    stage = nstage;
-    phase = nphase;
+  uint32_t phase = 0;  // of the chunk being consumed (stage = gc % STAGES, phase = (gc / STAGES) & 1, kept incrementally)
+  int gc = 0;
+  if (my_tiles > 0 && nchunks > 0) {
+    int64_t rt0, ct0;
+    tile_coords(0, rt0, ct0);
+    load_rows(rt0 * BR, a2, crow);
   }
 
-  // ---- epilogue ---------------------------------------------------------------------------------------------------
-  // Column map: thread (g,t) holds, for column pair pr, the 4 consecutive columns j0 + 16 pr + 4 t + {0,1,2,3} as
-  // acc[h][2pr][0], acc[h][2pr+1][0], acc[h][2pr][1], acc[h][2pr+1][1]; rows row0 + 8 (RT warp + h) + g.
-  if (BACKWARD) {
+#pragma unroll 1
+  for (int ti = 0; ti < my_tiles; ++ti) {
+    int64_t rt, ct;
+    tile_coords(ti, rt, ct);
+    const int64_t row0 = rt * BR;
+    const int64_t j0 = ct * BJ;
+    double* sY = sYall + (ti & 1) * 128;
+    if (!BACKWARD && !direct && tid < BR) sY[tid] = (row0 + tid < p.n_rows) ? p.y[row0 + tid] : 0.0;
+    double yreg[RT];  // direct Gaussian epilogue: the targets of this thread's rows (requested now, used after the main loop)
 #pragma unroll
     for (int h = 0; h < RT; ++h) {
       const int64_t r = row0 + (warp * RT + h) * 8 + g;
-      if (r >= p.n_rows) continue;
-      double* orow = p.out + ((int64_t)split * p.n_rows + r) * p.ldo;
+      yreg[h] = (!BACKWARD && deriv_direct && r < p.n_rows) ? p.y[r] : 0.0;
+    }
 #pragma unroll
-      for (int pr = 0; pr < NPR; ++pr) {
-        const int64_t col = j0 + 16 * pr + 4 * t;
-        double v[4] = {acc[h][2 * pr][0], acc[h][2 * pr + 1][0], acc[h][2 * pr][1], acc[h][2 * pr + 1][1]};
-        if (col + 3 < p.j) {
-          double2* dst = reinterpret_cast<double2*>(orow + col);
-          if (p.accumulate) {
-            const double2 o0 = dst[0], o1 = dst[1];
-            v[0] += o0.x;
-            v[1] += o0.y;
-            v[2] += o1.x;
-            v[3] += o1.y;
+    for (int h = 0; h < RT; ++h)
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        acc[h][nt][0] = 0.0;
+        acc[h][nt][1] = 0.0;
+      }
+
+    double kc[LA][2][RT];  // Gram values of the block being multiplied
+    if (nchunks > 0) {
+      mbar_wait(&full[stage], phase);
+      gram_block(sP + stage * BK * sp, 0, 2 * t, kc);
+    }
+#pragma unroll 1
+    for (int c = 0; c < nchunks; ++c, ++gc) {
+      // One iteration = one 32-point stage = 4 groups, fully unrolled (264 DMMAs).  The next stage was issued two chunk
+      // times ago; its Gram values (same tile only: they depend on the tile's rows) are formed before this stage's DMMAs.
+      const int nstage = (stage + 1 == STAGES) ? 0 : stage + 1;
+      const uint32_t nphase = (nstage == 0) ? (phase ^ 1u) : phase;
+      const bool more = c + 1 < nchunks;
+      const unsigned char* bchunk = sB + stage * STAGE_BYTES;
+      const double* Pt = sP + stage * BK * sp;
+      const int base = c * BK + 2 * t;  // this thread's first reduction point of the chunk, counted from `begin`
+#pragma unroll
+      for (int blk = 0; blk < NBLK; ++blk) {
+        double kn[LA][2][RT];  // the next block: of this chunk, or the first of the tile's next chunk
+        if (blk + 1 < NBLK) {
+          gram_block(Pt, (blk + 1) * LA, base + 8 * (blk + 1) * LA, kn);
+        } else if (more) {
+          mbar_wait(&full[nstage], nphase);
+          gram_block(sP + nstage * BK * sp, 0, base + BK, kn);
+        }
+#pragma unroll
+        for (int q = 0; q < LA; ++q) {
+          const unsigned char* bgrp = bchunk + (blk * LA + q) * 1024;
+          mma_step(bgrp + off0, kc[q][0]);
+          mma_step(bgrp + off1, kc[q][1]);
+        }
+        if (blk + 1 < NBLK || more) {
+#pragma unroll
+          for (int q = 0; q < LA; ++q)
+#pragma unroll
+            for (int h = 0; h < RT; ++h) {
+              kc[q][0][h] = kn[q][0][h];
+              kc[q][1][h] = kn[q][1][h];
+            }
+        }
+      }
+      // chunk gc fully consumed by this warp.  The last warp to release a stage refills it with chunk gc + STAGES (which may
+      // belong to a later tile of this CTA): nobody waits to issue a copy.  Forward role, last chunk of a tile: the refill is
+      // deferred until the epilogue has used the stage as its staging buffer.
+      __syncwarp();
+      if (lane == 0) {
+        if (atom_add_shared(&released[stage], 1u) == NWARPS - 1) {
+          released[stage] = 0;
+          if (gc + STAGES < total_gc && (BACKWARD || direct || more)) issue(gc + STAGES);
+        }
+      }
+      stage = nstage;
+      phase = nphase;
+    }
+    const int estage = (stage == 0) ? STAGES - 1 : stage - 1;  // the stage of the tile's last chunk
+
+    // ---- epilogue ---------------------------------------------------------------------------------------------------
+    // Column map: thread (g,t) holds, for column pair pr, the 4 consecutive columns j0 + 16 pr + 4 t + {0,1,2,3} as
+    // acc[h][2pr][0], acc[h][2pr+1][0], acc[h][2pr][1], acc[h][2pr+1][1]; rows row0 + 8 (RT warp + h) + g.
+    if (BACKWARD) {
+#pragma unroll
+      for (int h = 0; h < RT; ++h) {
+        const int64_t r = row0 + (warp * RT + h) * 8 + g;
+        if (r >= p.n_rows) continue;
+        double* orow = p.out + ((int64_t)split * p.n_rows + r) * p.ldo;
+#pragma unroll
+        for (int pr = 0; pr < NPR; ++pr) {
+          const int64_t col = j0 + 16 * pr + 4 * t;
+          double v[4] = {acc[h][2 * pr][0], acc[h][2 * pr + 1][0], acc[h][2 * pr][1], acc[h][2 * pr + 1][1]};
+          if (col + 3 < p.j) {
+            double2* dst = reinterpret_cast<double2*>(orow + col);
+            if (p.accumulate) {
+              const double2 o0 = dst[0], o1 = dst[1];
+              v[0] += o0.x;
+              v[1] += o0.y;
+              v[2] += o1.x;
+              v[3] += o1.y;
+            }
+            dst[0] = make_double2(v[0], v[1]);
+            dst[1] = make_double2(v[2], v[3]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (col + e < p.j) orow[col + e] = p.accumulate ? orow[col + e] + v[e] : v[e];
           }
-          dst[0] = make_double2(v[0], v[1]);
-          dst[1] = make_double2(v[2], v[3]);
-        } else {
-#pragma unroll
-          for (int e = 0; e < 4; ++e)
-            if (col + e < p.j) orow[col + e] = p.accumulate ? orow[col + e] + v[e] : v[e];
         }
       }
+      return;
     }
-    return;
-  }
 
-  // Forward role: stage the F tile in shared memory (the pipeline buffers are idle: every issued copy has landed and been
-  // consumed), then one coalesced pass applies the cost functor -- inlined once, in a rolled loop with independent
-  // evaluations in flight -- and writes whole 128-byte lines.
-  __syncthreads();
-  double* sF = reinterpret_cast<double*>(sB);  // [BR][SF]
+    if (direct) {
 #pragma unroll
-  for (int h = 0; h < RT; ++h) {
-    double* frow = sF + ((warp * RT + h) * 8 + g) * SF + 4 * t;
+      for (int h = 0; h < RT; ++h) {
+        const int64_t r = row0 + (warp * RT + h) * 8 + g;
+        if (r >= p.n_rows) continue;
+        double* orow = p.out + r * p.ldo + j0;
+        const int64_t cols_here = (p.j - j0 < BJ) ? (p.j - j0) : BJ;
 #pragma unroll
-    for (int pr = 0; pr < NPR; ++pr) {
-      double2* dst = reinterpret_cast<double2*>(frow + 16 * pr);
-      dst[0] = make_double2(acc[h][2 * pr][0], acc[h][2 * pr + 1][0]);
-      dst[1] = make_double2(acc[h][2 * pr][1], acc[h][2 * pr + 1][1]);
+        for (int pr = 0; pr < NPR; ++pr) {
+          const int col = 16 * pr + 4 * t;
+          double v[4] = {acc[h][2 * pr][0], acc[h][2 * pr + 1][0], acc[h][2 * pr][1], acc[h][2 * pr + 1][1]};
+          if (gauss_direct) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[e] = inv_noise * (v[e] - yreg[h]);
+          } else if (deriv_direct) {
+            const D4 d = cost_derivative4(sCost, yreg[h], D4{v[0], v[1], v[2], v[3]});
+            v[0] = d.a;
+            v[1] = d.b;
+            v[2] = d.c;
+            v[3] = d.d;
+          }
+          if (col + 3 < cols_here) {
+            if (wide_store) {
+              asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(orow + col), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]) : "memory");
+            } else {
+              double2* dst = reinterpret_cast<double2*>(orow + col);
+              dst[0] = make_double2(v[0], v[1]);
+              dst[1] = make_double2(v[2], v[3]);
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (col + e < cols_here) orow[col + e] = v[e];
+          }
+        }
+      }
+      if (ti + 1 < my_tiles) {
+        int64_t rtn, ctn;
+        tile_coords(ti + 1, rtn, ctn);
+        load_rows(rtn * BR, a2, crow);
+      }
+      continue;
     }
-  }
-  __syncthreads();
-  const int64_t rows_here = (p.n_rows - row0 < BR) ? (p.n_rows - row0) : BR;
-  const int64_t cols_here = (p.j - j0 < BJ) ? (p.j - j0) : BJ;
 
-  if (p.epilogue == PLS_EPI_COST) {
-    // per-column sum over this tile's rows (increasing row order) of c(y_n, F[n][j]) -> out[rt][j]
-    if (tid < cols_here) {
-      double v = 0.0;
-      for (int r = 0; r < (int)rows_here; ++r) v += cost_value(p.cost, sY[r], sF[r * SF + tid]);
-      p.out[rt * p.ldo + j0 + tid] = v;
+    // Forward role, staged epilogue.  The next tile's row fragments are pulled into L2 now; they are loaded once the
+    // accumulators are dead.
+    int64_t next_row0 = 0;
+    if (ti + 1 < my_tiles) {
+      int64_t rtn, ctn;
+      tile_coords(ti + 1, rtn, ctn);
+      next_row0 = rtn * BR;
+      const int64_t r = next_row0 + warp * RT * 8 + g;
+      if (r < p.n_rows) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.rows_aug + r * sp + 4 * t));
     }
-    return;
-  }
-
-  const bool dcost = (p.epilogue != PLS_EPI_PREDICTION);
-  const bool with_cost = (p.epilogue == PLS_EPI_COST_DERIVATIVE_AND_COST);
-  constexpr int PAIRS = BJ / 2;                 // double2 per row
-  constexpr int PHASES = NTHREADS / PAIRS;      // a thread keeps its column pair and visits rows phase, phase + PHASES, ...
-  const int col = 2 * (tid % PAIRS);
-  const int rphase = tid / PAIRS;
-  double csum0 = 0.0, csum1 = 0.0;              // cost of this thread's two columns over its rows, increasing row order
-  if (col < cols_here) {
+    // The F tile goes through the stage the tile's last chunk occupied (the other two stages already receive the next
+    // tile's first chunks), 32 rows at a time, 16-byte chunks XOR-swizzled with the row parity (conflict-free both ways);
+    // a coalesced pass then applies the cost functor -- inlined once, rolled loop -- and writes whole 128-byte lines.
+    const int64_t rows_here = (p.n_rows - row0 < BR) ? (p.n_rows - row0) : BR;
+    const int64_t cols_here = (p.j - j0 < BJ) ? (p.j - j0) : BJ;
+    const bool dcost = (p.epilogue == PLS_EPI_COST_DERIVATIVE || p.epilogue == PLS_EPI_COST_DERIVATIVE_AND_COST);
+    const bool with_cost = (p.epilogue == PLS_EPI_COST || p.epilogue == PLS_EPI_COST_DERIVATIVE_AND_COST);
+    const bool store = (p.epilogue != PLS_EPI_COST);
+    constexpr int PAIRS = BJ / 2;             // double2 per row
+    constexpr int PHASES = NTHREADS / PAIRS;  // a thread keeps its column pair and visits rows rphase, rphase + PHASES, ...
+    constexpr int PASS_ROWS = 32;
+    constexpr int NPASS = BR / PASS_ROWS;
+    unsigned char* sF = sB + estage * STAGE_BYTES;  // [32 rows][BJ doubles], chunk index ^= row & 1
+    const int col = 2 * (tid % PAIRS);
+    const int rphase = tid / PAIRS;
+    double csum0 = 0.0, csum1 = 0.0;  // cost of this thread's two columns over its rows, increasing row order
+#pragma unroll 1
+    for (int pass = 0; pass < NPASS; ++pass) {
+      __syncthreads();  // pass 0: every warp has left the main loop (the stage is free); later: the previous pass was read
+#pragma unroll
+      for (int h = 0; h < RT; ++h) {
+        const int lr = (warp * RT + h) * 8 + g - pass * PASS_ROWS;  // row within the pass
+        if (lr >= 0 && lr < PASS_ROWS) {
+          unsigned char* frow = sF + (size_t)lr * (BJ * 8);
+#pragma unroll
+          for (int pr = 0; pr < NPR; ++pr) {
+            const int ch = 8 * pr + 2 * t;  // 16-byte chunk of columns 16 pr + 4 t (+1); the next chunk holds (+2, +3)
+            *reinterpret_cast<double2*>(frow + ((ch ^ (lr & 1)) << 4)) = make_double2(acc[h][2 * pr][0], acc[h][2 * pr + 1][0]);
+            *reinterpret_cast<double2*>(frow + (((ch + 1) ^ (lr & 1)) << 4)) = make_double2(acc[h][2 * pr][1], acc[h][2 * pr + 1][1]);
+          }
+        }
+      }
+      __syncthreads();
+      if (col < cols_here) {
 #pragma unroll 2
-    for (int r = rphase; r < (int)rows_here; r += PHASES) {
-      double2 v = *reinterpret_cast<const double2*>(sF + r * SF + col);
-      if (dcost) {
-        const double yv = sY[r];
-        if (with_cost) {
-          csum0 += cost_value(p.cost, yv, v.x);
-          csum1 += cost_value(p.cost, yv, v.y);
+        for (int lr = rphase; lr < PASS_ROWS; lr += PHASES) {
+          const int r = pass * PASS_ROWS + lr;
+          if (r >= rows_here) break;
+          double2 v = *reinterpret_cast<const double2*>(sF + (size_t)lr * (BJ * 8) + ((((col >> 1)) ^ (lr & 1)) << 4));
+          const double yv = (dcost || with_cost) ? sY[r] : 0.0;
+          if (with_cost) {
+            csum0 += cost_value(p.cost, yv, v.x);
+            csum1 += cost_value(p.cost, yv, v.y);
+          }
+          if (store) {
+            if (dcost) {
+              v.x = cost_derivative(p.cost, yv, v.x);
+              v.y = cost_derivative(p.cost, yv, v.y);
+            }
+            double* dst = p.out + (row0 + r) * p.ldo + j0 + col;
+            if (col + 1 < cols_here) *reinterpret_cast<double2*>(dst) = v;
+            else dst[0] = v.x;
+          }
         }
-        v.x = cost_derivative(p.cost, yv, v.x);
-        v.y = cost_derivative(p.cost, yv, v.y);
       }
-      double* dst = p.out + (row0 + r) * p.ldo + j0 + col;
-      if (col + 1 < cols_here) *reinterpret_cast<double2*>(dst) = v;
-      else dst[0] = v.x;
     }
-  }
-  if (with_cost) {
-    double* sC = sF + BR * SF;  // [PHASES][BJ] scratch behind the staged tile
-    sC[rphase * BJ + col] = csum0;
-    sC[rphase * BJ + col + 1] = csum1;
-    __syncthreads();
-    if (tid < cols_here) {
+    if (with_cost) {  // per-column sums over the tile's rows -> (tiles x J): PLS_EPI_COST writes out, the fused epilogue out2
+      sC[rphase * BJ + col] = csum0;
+      sC[rphase * BJ + col + 1] = csum1;
+    }
+    __syncthreads();  // the staging stage has been read; sC is complete
+    if (with_cost && tid < cols_here) {
       double v = 0.0;
 #pragma unroll
       for (int ph = 0; ph < PHASES; ++ph) v += sC[ph * BJ + tid];
-      p.out2[rt * p.ldo2 + j0 + tid] = v;
+      if (p.epilogue == PLS_EPI_COST) p.out[rt * p.ldo + j0 + tid] = v;
+      else p.out2[rt * p.ldo2 + j0 + tid] = v;
     }
+    if (tid == 0 && gc - 1 + STAGES < total_gc) {  // (staged epilogue only: the direct one never defers)
+      fence_proxy_async();  // the staging writes (generic proxy) are ordered before the copy (async proxy) into the same stage
+      issue(gc - 1 + STAGES);  // the refill deferred at the tile's last chunk
+    }
+    if (ti + 1 < my_tiles) load_rows(next_row0, a2, crow);
   }
 }
 
@@ -418,6 +552,7 @@ cudaError_t launch_one(const pls_ctx* ctx, GenGemmParams p, cudaStream_t stream)
   using T = Tile<RT>;
   int64_t grid = ((p.n_rows + T::BR - 1) / T::BR) * ((p.j + T::BJ - 1) / T::BJ);
   if (BACKWARD) grid *= p.splits;
+  else if (grid > ctx->sm_count) grid = ctx->sm_count;  // persistent forward: one CTA per SM walks the tiles
   if (grid <= 0 || p.red_total <= 0) return cudaSuccess;
   if (grid > 2147483647LL) return cudaErrorInvalidConfiguration;
   const size_t smem = gen_gemm_smem_bytes<RT>(p.sp);
