@@ -15,32 +15,68 @@ namespace pls {
 
 __device__ __forceinline__ double clip(double v, double lo, double hi) { return fmin(fmax(v, lo), hi); }
 
-__device__ __forceinline__ double link_transform(const pls_cost& c, double f) {
+// Arithmetic policies of the derivative functors.
+//   LibMath : CUDA's IEEE double division and exp (<= 1 ulp).  Both contain a rarely taken branch / slow-path call, which
+//             turns every evaluation into several basic blocks: independent evaluations cannot interleave.
+//   FlatMath: branch-free equivalents for the register epilogue of the hot kernel, where four evaluations per call must
+//             overlap their dependent FP64 chains.  div: MUFU.RCP64H seed, two Newton steps, one residual correction
+//             (<= 1 ulp; +-0 and +-inf divisors give the IEEE results by selection; a denormal divisor is treated as 0);
+//             exp: the hot loop's table-driven routine (<= 2 ulp), +inf above 709.78, clamped below -700.
+struct LibMath {
+  __device__ __forceinline__ double div(double a, double b) const { return a / b; }
+  __device__ __forceinline__ double expo(double x) const { return exp(x); }
+};
+struct FlatMath {
+  const double* tbl;  // 2^(j/64), j = 0..63, in shared memory
+  __device__ __forceinline__ double div(double a, double b) const {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+    double e = fma(-b, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-b, r, 1.0);
+    r = fma(r, e, r);
+    double q = a * r;
+    q = fma(fma(-b, q, a), r, q);
+    const double ab = fabs(b);
+    // a / +-0 = a * +-inf,  a / +-inf = a * +-0   (NaN where IEEE gives NaN)
+    q = (ab < 2.2250738585072014e-308) ? a * copysign(__longlong_as_double(0x7ff0000000000000LL), b) : q;
+    q = (ab > 1.7976931348623157e308) ? a * copysign(0.0, b) : q;
+    return q;
+  }
+  __device__ __forceinline__ double expo(double x) const {
+    const double v = gram_exp_fast(fmin(x, 709.782712893384), tbl);
+    return (x > 709.782712893384) ? __longlong_as_double(0x7ff0000000000000LL) : ((x != x) ? x : v);
+  }
+};
+
+template <class M = LibMath>
+__device__ __forceinline__ double link_transform(const pls_cost& c, double f, const M& m = M()) {
   switch (c.link_id) {
     case PLS_LINK_SQUARE:
       return f * f;
     case PLS_LINK_SIGMOID:
-      return clip(1.0 / (1.0 + exp(-f)), c.link_jitter, 1.0 - c.link_jitter);
+      return clip(m.div(1.0, 1.0 + m.expo(-f)), c.link_jitter, 1.0 - c.link_jitter);
     case PLS_LINK_PROBIT:
-      return clip((1.0 + erf(f / c.probit_divisor)) / 2.0, c.link_jitter, 1.0 - c.link_jitter);
+      return clip((1.0 + erf(m.div(f, c.probit_divisor))) / 2.0, c.link_jitter, 1.0 - c.link_jitter);
     default:
       return f;
   }
 }
 
-__device__ __forceinline__ double link_derivative(const pls_cost& c, double f) {
+template <class M = LibMath>
+__device__ __forceinline__ double link_derivative(const pls_cost& c, double f, const M& m = M()) {
   switch (c.link_id) {
     case PLS_LINK_SQUARE:
       return 2.0 * f;
     case PLS_LINK_SIGMOID: {
-      const double s = 1.0 / (1.0 + exp(-f));
+      const double s = m.div(1.0, 1.0 + m.expo(-f));
       return (s >= c.link_jitter && s <= 1.0 - c.link_jitter) ? s * (1.0 - s) : 0.0;
     }
     case PLS_LINK_PROBIT: {
-      const double u = f / c.probit_divisor;
+      const double u = m.div(f, c.probit_divisor);
       const double p = (1.0 + erf(u)) / 2.0;
       // d/df [ (1 + erf(f / r)) / 2 ] = exp(-(f/r)^2) / (r sqrt(pi))
-      return (p >= c.link_jitter && p <= 1.0 - c.link_jitter) ? exp(-u * u) / (c.probit_divisor * 1.7724538509055160273) : 0.0;
+      return (p >= c.link_jitter && p <= 1.0 - c.link_jitter) ? m.div(m.expo(-u * u), c.probit_divisor * 1.7724538509055160273) : 0.0;
     }
     default:
       return 1.0;
@@ -77,41 +113,42 @@ __device__ __forceinline__ double cost_value(const pls_cost& c, double y, double
 }
 
 // d c(y, F) / d F for one training point
-__device__ __forceinline__ double cost_derivative(const pls_cost& c, double y, double f) {
+template <class M = LibMath>
+__device__ __forceinline__ double cost_derivative(const pls_cost& c, double y, double f, const M& m = M()) {
   if (c.closed_form) {
-    if (c.cost_id == PLS_COST_GAUSSIAN && c.link_id == PLS_LINK_IDENTITY) return (1.0 / c.observation_noise) * (f - y);
+    if (c.cost_id == PLS_COST_GAUSSIAN && c.link_id == PLS_LINK_IDENTITY) return m.div(1.0, c.observation_noise) * (f - y);
     if (c.cost_id == PLS_COST_BERNOULLI && c.link_id == PLS_LINK_SIGMOID) {
-      const double p = link_transform(c, f);  // the clipped probability, as bernoulli.py:72-77 uses it
+      const double p = link_transform(c, f, m);  // the clipped probability, as bernoulli.py:72-77 uses it
       return -(y * (1.0 - p)) + (1.0 - y) * p;
     }
-    if (c.cost_id == PLS_COST_POISSON && c.link_id == PLS_LINK_SQUARE) return -2.0 * (y / f) + 2.0 * f;
+    if (c.cost_id == PLS_COST_POISSON && c.link_id == PLS_LINK_SQUARE) return -2.0 * m.div(y, f) + 2.0 * f;
     if (c.cost_id == PLS_COST_STUDENT_T && c.link_id == PLS_LINK_IDENTITY) {
       const double e = f - y;
-      return (c.degrees_of_freedom + 1.0) * (e / (c.degrees_of_freedom * (c.scale * c.scale) + e * e));
+      return (c.degrees_of_freedom + 1.0) * m.div(e, c.degrees_of_freedom * (c.scale * c.scale) + e * e);
     }
   }
-  const double mu = link_transform(c, f);
-  const double dmu = link_derivative(c, f);
+  const double mu = link_transform(c, f, m);
+  const double dmu = link_derivative(c, f, m);
   switch (c.cost_id) {
     case PLS_COST_GAUSSIAN:
-      return (mu - y) / c.observation_noise * dmu;
+      return m.div(mu - y, c.observation_noise) * dmu;
     case PLS_COST_BERNOULLI:
-      return (-y / mu + (1.0 - y) / (1.0 - mu)) * dmu;
+      return (m.div(-y, mu) + m.div(1.0 - y, 1.0 - mu)) * dmu;
     case PLS_COST_POISSON:
-      return -2.0 * y / f + dmu;
+      return m.div(-2.0 * y, f) + dmu;
     case PLS_COST_STUDENT_T: {
       const double e = mu - y;
-      return (c.degrees_of_freedom + 1.0) * e / (c.degrees_of_freedom * c.scale * c.scale + e * e) * dmu;
+      return m.div((c.degrees_of_freedom + 1.0) * e, c.degrees_of_freedom * c.scale * c.scale + e * e) * dmu;
     }
     case PLS_COST_MULTIMODAL: {
       const double s2 = c.observation_noise * c.observation_noise;
       const double e1 = y - mu + c.shift;
       const double e2 = y - mu;
-      const double a1 = c.log_weight_1 - 0.5 * e1 * e1 / s2;
-      const double a2 = c.log_weight_2 - 0.5 * e2 * e2 / s2;
+      const double a1 = c.log_weight_1 - m.div(0.5 * e1 * e1, s2);
+      const double a2 = c.log_weight_2 - m.div(0.5 * e2 * e2, s2);
       const double mx = fmax(a1, a2);
-      const double w1 = exp(a1 - mx), w2 = exp(a2 - mx);
-      return -((w1 * e1 + w2 * e2) / (w1 + w2)) / s2 * dmu;
+      const double w1 = m.expo(a1 - mx), w2 = m.expo(a2 - mx);
+      return m.div(-m.div(w1 * e1 + w2 * e2, w1 + w2), s2) * dmu;
     }
   }
   return 0.0;

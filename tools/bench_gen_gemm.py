@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--splits", type=int, default=0)
     ap.add_argument("--kernel", type=str, default="rbf", choices=["rbf", "linear"])
+    ap.add_argument("--cost", type=str, default="gaussian", choices=["gaussian", "poisson", "bernoulli", "student_t", "multimodal"])
     ap.add_argument("--roles", type=str, default="forward,backward")
     args = ap.parse_args()
 
@@ -44,6 +45,18 @@ def main():
     y = torch.randn(n, generator=g, dtype=torch.float64).cuda()
     cost = nat.PlsCost()
     cost.cost_id, cost.link_id, cost.closed_form, cost.observation_noise = nat.COST_GAUSSIAN, nat.LINK_IDENTITY, 1, 0.01
+    cost.link_jitter, cost.probit_divisor, cost.degrees_of_freedom, cost.scale = 1e-10, 2.0 ** 0.5, 4.0, 0.7
+    cost.shift, cost.bernoulli_noise, cost.log_weight_1, cost.log_weight_2, cost.log_normaliser = 1.0, 0.3, -1.2, -0.36, 0.0
+    if args.cost == "poisson":
+        cost.cost_id, cost.link_id = nat.COST_POISSON, nat.LINK_SQUARE
+        y = torch.poisson(torch.full((n,), 3.0, dtype=torch.float64), generator=g).cuda()
+    elif args.cost == "bernoulli":
+        cost.cost_id, cost.link_id = nat.COST_BERNOULLI, nat.LINK_SIGMOID
+        y = (torch.rand(n, generator=g, dtype=torch.float64) > 0.5).double().cuda()
+    elif args.cost == "student_t":
+        cost.cost_id = nat.COST_STUDENT_T
+    elif args.cost == "multimodal":
+        cost.cost_id, cost.closed_form, cost.observation_noise = nat.COST_MULTIMODAL, 0, 0.5
     tile_rows = ops.forward_tile_rows(ctx, j)
     out_rows = (n + tile_rows - 1) // tile_rows if args.epilogue == nat.EPI_COST else n
     out = torch.zeros(out_rows, j, dtype=torch.float64).cuda()
@@ -51,7 +64,7 @@ def main():
     splits = args.splits or ops.backward_splits(ctx, n, m, j)
     gp = torch.zeros(splits, m, j, dtype=torch.float64).cuda()
     flops = 2.0 * n * m * j
-    res = {"n": n, "m": m, "d": d, "j": j, "rt": args.rt, "epilogue": args.epilogue, "kernel": args.kernel, "splits": splits}
+    res = {"n": n, "m": m, "d": d, "j": j, "rt": args.rt, "epilogue": args.epilogue, "kernel": args.kernel, "cost": args.cost, "splits": splits}
 
     def timed(fn):
         fn()
