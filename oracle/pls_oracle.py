@@ -493,6 +493,33 @@ def train_pls_oracle(pls: "PLSOracle", particles: torch.Tensor, number_of_epochs
     return particles, energy_potentials
 
 
+def train_pls_runner_oracle(pls: "PLSOracle", particles: torch.Tensor, simulation_duration: float, maximum_number_of_steps: int,
+                            early_stopper_patience: float, number_of_step_searches: int, step_size_upper: float,
+                            minimum_change_in_energy_potential: float, seed: int):
+    """experiments/runners.py:331-446 with metric_to_optimise="loss" (the final energy potential): log-spaced step sizes from
+    step_size_upper down to simulation_duration / maximum_number_of_steps, every run restarted from the same particles under
+    set_seed(seed), best = lowest final energy among finite runs, early exit when two consecutive step sizes end within
+    `minimum_change_in_energy_potential` (relative) of each other.  Parity unpinned against the reference's own runner
+    (its module imports matplotlib / sklearn plotting code that is absent here); restated line by line."""
+    best_metric_value, best_lr = float("inf"), None
+    history = {}
+    step_sizes = np.logspace(np.log10(step_size_upper), np.log10(simulation_duration / maximum_number_of_steps), number_of_step_searches)
+    particles_out = particles.detach().clone()
+    for i, step_size in enumerate(step_sizes):
+        number_of_epochs = int(simulation_duration / step_size)
+        set_seed(seed)
+        particles_i, energies = train_pls_oracle(pls, particles.detach().clone(), number_of_epochs, step_size, early_stopper_patience)
+        if energies and torch.isfinite(particles_i).all():
+            history[step_size] = energies
+            metric_value = energies[-1]
+            if metric_value < best_metric_value:
+                best_metric_value, best_lr, particles_out = metric_value, step_size, particles_i.detach().clone()
+            if (i > 0 and step_sizes[i - 1] in history
+                    and abs(history[step_sizes[i - 1]][-1] - energies[-1]) / history[step_sizes[i - 1]][-1] < minimum_change_in_energy_potential):
+                break
+    return particles_out, best_lr, len(history[best_lr]), history
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # ConditionalVariance inducing-point selector -- src/inducing_point_selectors/conditional_variance.py:27-120
 # ----------------------------------------------------------------------------------------------------------------

@@ -604,3 +604,32 @@ def test_predict_untransformed_samples_matches_oracle(b200):
     want = orc.basis.predict_untransformed_samples(p, xs, noise=noise)
     got = pls.predict_untransformed_samples(p.cuda(), xs, noise=noise)
     assert rel_err(got, want) < TOL
+
+
+def test_step_size_search_runner_and_checkpoint(b200, tmp_path):
+    """runners.train_pls_runner (experiments/runners.py:331-446, metric "loss") against the oracle's restatement: same best
+    step size, same number of accepted epochs, same particles; then the reference's .pth checkpoint format round-trips."""
+    from oracle.pls_oracle import train_pls_runner_oracle
+    from projected_langevin_sampling_b200.runners import load_pls, save_pls, train_pls_runner
+
+    torch.set_default_dtype(torch.float64)
+    try:
+        x, y, z, ls, g = _problem(400, 2, 12, 16, seed=33)
+        pls, orc = _build_pair(b200, x, y, z, ls, 1.2, "gaussian", "identity", threshold=1e-6)
+        p0 = torch.randn(orc.basis.approximation_dimension, 16, generator=g, dtype=torch.float64)
+        kw = dict(simulation_duration=0.02, maximum_number_of_steps=40, early_stopper_patience=1.0, number_of_step_searches=4,
+                  step_size_upper=5e-3, minimum_change_in_energy_potential=1e-9, seed=3)
+        want_p, want_lr, want_n, want_hist = train_pls_runner_oracle(orc, p0.clone(), **kw)
+        hist = {}
+        got_p, got_lr, got_n = train_pls_runner(pls, p0.cuda(), energy_potentials_history=hist, **kw)
+        assert got_lr == want_lr and got_n == want_n and list(hist) == list(want_hist)
+        for step_size in hist:
+            assert np.allclose(hist[step_size], want_hist[step_size], rtol=1e-9)
+        assert rel_err(got_p, want_p) < 1e-9
+        path = str(tmp_path / "pls.pth")
+        save_pls(pls, got_p, path, best_lr=got_lr, number_of_epochs=got_n)
+        pls.observation_noise = 123.0
+        pls2, p2, lr2, n2 = load_pls(pls, path)
+        assert torch.equal(p2, got_p) and lr2 == got_lr and n2 == got_n and pls2.observation_noise == 0.25
+    finally:
+        torch.set_default_dtype(torch.float32)
