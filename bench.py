@@ -209,7 +209,7 @@ def run_reference_arm(args, workload):
         "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": time.perf_counter() - t0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---- FP64 peak -----------------------------------------------------------------------------------------------------------
@@ -285,7 +285,27 @@ class KernelTimer:
         return out
 
 
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """stdout carries exactly ONE JSON line.  Libraries write there too (NCCL prints its version from C when NCCL_DEBUG is
+    set on the box), so file descriptor 1 is pointed at stderr for the whole run and the line goes to a saved duplicate."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -483,7 +503,7 @@ def main():
                    "particles_finite": finite, "setup_s": setup_s},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
 

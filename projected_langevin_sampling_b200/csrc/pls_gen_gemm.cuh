@@ -574,7 +574,12 @@ cudaError_t launch_one(const pls_ctx* ctx, GenGemmParams p, cudaStream_t stream)
   using T = Tile<RT>;
   int64_t grid = ((p.n_rows + T::BR - 1) / T::BR) * ((p.j + T::BJ - 1) / T::BJ);
   if (BACKWARD) grid *= p.splits;
-  else if (grid > ctx->sm_count) grid = ctx->sm_count;  // persistent forward: one CTA per SM walks the tiles
+  else {
+    const int64_t tiles = grid;
+    if (grid > ctx->sm_count) grid = ctx->sm_count;  // persistent forward: one CTA per SM walks the tiles
+    // the kernel counts the chunks a CTA streams over all its tiles in 32 bits
+    if (grid > 0 && ((tiles + grid - 1) / grid) * ((p.red_total + BK - 1) / BK) > 2147483647LL) return cudaErrorInvalidConfiguration;
+  }
   if (grid <= 0 || p.red_total <= 0) return cudaSuccess;
   if (grid > 2147483647LL) return cudaErrorInvalidConfiguration;
   const size_t smem = gen_gemm_smem_bytes<RT>(p.sp);
