@@ -192,8 +192,8 @@ __global__ void __launch_bounds__(128) small_gemm_kernel(const SmallGemmParams p
   }
 
   const double sq2eta = sqrt(2.0 * p.eta);
-#pragma unroll
   const uint64_t step = (UPDATE && p.step_counter) ? p.step + *p.step_counter : p.step;
+#pragma unroll
   for (int mt = 0; mt < 4; ++mt) {
     const int64_t r = row0 + wm * 32 + mt * 8 + g;
     if (r >= p.rows) continue;
