@@ -49,13 +49,14 @@ def _units():
     units = [("pls_api.cu", [], "pls_api.o"), ("pls_aux.cu", [], "pls_aux.o"), ("pls_selector.cu", [], "pls_selector.o"),
              ("pls_gen_gemm.cu", [], "pls_gen_gemm.o")]
     for k in range(1, MAX_NKD + 1):
-        units.append(("pls_gen_gemm_inst.cu", [f"-DPLS_NKD={k}"], f"pls_gen_gemm_nkd{k}.o"))
+        for role in range(5):  # forward epilogues PLS_EPI_* (0..3), backward (4)
+            units.append(("pls_gen_gemm_inst.cu", [f"-DPLS_NKD={k}", f"-DPLS_ROLE={role}"], f"pls_gen_gemm_nkd{k}_role{role}.o"))
     return units
 
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
     """Compile (if sources changed) and return the path of libpls_b200.so."""
-    stamp = os.path.join(BUILD, "source.sha256")
+    stamp = LIB + ".sha256"  # next to the library (csrc/build/ does not travel to the GPU box)
     digest = _source_hash()
     if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read().strip() == digest:
         return LIB

@@ -50,31 +50,33 @@ cudaError_t make_stream_maps(const pls_ctx*, const double* b, int64_t rows, int6
   return cudaSuccess;
 }
 
-#define PLS_DECL(k) \
-  cudaError_t launch_gen_gemm_nkd##k(bool backward, const pls_ctx* ctx, const GenGemmParams& p, cudaStream_t stream);
+#define PLS_DECL_ROLE(k, r) \
+  cudaError_t launch_gen_gemm_nkd##k##_role##r(const pls_ctx* ctx, const GenGemmParams& p, cudaStream_t stream);
+#define PLS_DECL(k) PLS_DECL_ROLE(k, 0) PLS_DECL_ROLE(k, 1) PLS_DECL_ROLE(k, 2) PLS_DECL_ROLE(k, 3) PLS_DECL_ROLE(k, 4)
 PLS_DECL(1) PLS_DECL(2) PLS_DECL(3) PLS_DECL(4) PLS_DECL(5) PLS_DECL(6) PLS_DECL(7)
 #undef PLS_DECL
+#undef PLS_DECL_ROLE
 
-static cudaError_t dispatch(bool backward, const pls_ctx* ctx, const GenGemmParams& p, cudaStream_t stream) {
-  if (p.rt != 1 && p.rt != 2) return cudaErrorInvalidValue;
-  switch (point_ksteps(p.d)) {
-    case 1: return launch_gen_gemm_nkd1(backward, ctx, p, stream);
-    case 2: return launch_gen_gemm_nkd2(backward, ctx, p, stream);
-    case 3: return launch_gen_gemm_nkd3(backward, ctx, p, stream);
-    case 4: return launch_gen_gemm_nkd4(backward, ctx, p, stream);
-    case 5: return launch_gen_gemm_nkd5(backward, ctx, p, stream);
-    case 6: return launch_gen_gemm_nkd6(backward, ctx, p, stream);
-    case 7: return launch_gen_gemm_nkd7(backward, ctx, p, stream);
-    default: return cudaErrorInvalidValue;
-  }
+using Launcher = cudaError_t (*)(const pls_ctx*, const GenGemmParams&, cudaStream_t);
+#define PLS_ROW(k) {launch_gen_gemm_nkd##k##_role0, launch_gen_gemm_nkd##k##_role1, launch_gen_gemm_nkd##k##_role2, \
+                    launch_gen_gemm_nkd##k##_role3, launch_gen_gemm_nkd##k##_role4}
+static const Launcher kLaunchers[MAX_NKD][5] = {PLS_ROW(1), PLS_ROW(2), PLS_ROW(3), PLS_ROW(4), PLS_ROW(5), PLS_ROW(6), PLS_ROW(7)};
+#undef PLS_ROW
+
+// role: 0..3 = forward epilogue PLS_EPI_*, 4 = backward
+static cudaError_t dispatch(int role, const pls_ctx* ctx, const GenGemmParams& p, cudaStream_t stream) {
+  if ((p.rt != 1 && p.rt != 2) || role < 0 || role > 4) return cudaErrorInvalidValue;
+  const int nkd = point_ksteps(p.d);
+  if (nkd < 1 || nkd > MAX_NKD) return cudaErrorInvalidValue;
+  return kLaunchers[nkd - 1][role](ctx, p, stream);
 }
 
 cudaError_t launch_gen_gemm_forward(const pls_ctx* ctx, const GenGemmParams& p, cudaStream_t stream) {
-  return dispatch(false, ctx, p, stream);
+  return dispatch(p.epilogue, ctx, p, stream);
 }
 
 cudaError_t launch_gen_gemm_backward(const pls_ctx* ctx, const GenGemmParams& p, cudaStream_t stream) {
-  return dispatch(true, ctx, p, stream);
+  return dispatch(4, ctx, p, stream);
 }
 
 }  // namespace pls

@@ -79,6 +79,17 @@ static __device__ __noinline__ D4 cost_derivative4(const pls_cost* c, const doub
   return f;
 }
 
+// Four cost VALUES per call (the energy's cost sums); log() keeps CUDA's implementation.
+static __device__ __noinline__ D4 cost_value4(const pls_cost* c, double y, D4 f) {
+  const pls_cost cc = *c;
+  D4 r;
+  r.a = cost_value(cc, y, f.a);
+  r.b = cost_value(cc, y, f.b);
+  r.c = cost_value(cc, y, f.c);
+  r.d = cost_value(cc, y, f.d);
+  return r;
+}
+
 template <int RT>
 struct Tile {
   static constexpr int NT = 32 / RT;          // n8 column tiles per warp
@@ -99,6 +110,12 @@ __host__ __device__ inline size_t gen_gemm_smem_bytes(int sp) {
   const size_t cost_scratch = sizeof(double) * 2 * NTHREADS;  // [PHASES][BJ]
   return 1024 /* alignment slack */ + SMEM_HEADER + pipeline + cost_scratch;
 }
+// with room for the per-warp cost sums [NWARPS][BJ] of the register cost-sum epilogue (shares the scratch region)
+template <int RT>
+__host__ __device__ inline size_t gen_gemm_smem_bytes_wbuf(int sp) {
+  const size_t pipeline = (size_t)STAGES * Tile<RT>::STAGE_BYTES + sizeof(double) * (size_t)(STAGES * BK * sp);
+  return 1024 + SMEM_HEADER + pipeline + sizeof(double) * (size_t)(NWARPS * Tile<RT>::BJ);
+}
 
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar) {
   asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
@@ -112,6 +129,11 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, in
                "l"(tm), "r"(c0), "r"(c1), "r"(smem_u32(bar))
                : "memory");
 }
+__device__ __forceinline__ unsigned atom_add_acq_rel_shared(unsigned* addr, unsigned v) {
+  unsigned old;
+  asm volatile("atom.acq_rel.cta.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(addr)), "r"(v) : "memory");
+  return old;
+}
 // Stage-release counter.  Relaxed on purpose: a warp reaches this only after the DMMAs that consumed its LDS data of the
 // stage have issued (in-order issue: the loads have returned), so when the last warp sees the count the stage is no longer
 // being read and the tensor-map copy may overwrite it; acq_rel would put a MEMBAR in front of every release.
@@ -121,7 +143,9 @@ __device__ __forceinline__ unsigned atom_add_shared(unsigned* addr, unsigned v) 
   return old;
 }
 
-template <int NKD, bool BACKWARD, bool RBF, int RT>
+// EPI: the forward epilogue (PLS_EPI_*), a template parameter so that every kernel carries only its own epilogue's code and
+// register budget; the backward role is instantiated with EPI = -1.
+template <int NKD, bool BACKWARD, bool RBF, int RT, int EPI>
 __global__ void __launch_bounds__(NTHREADS, 1)
     gen_gemm_kernel(const GenGemmParams p, const __grid_constant__ CUtensorMap tm3, const __grid_constant__ CUtensorMap tm2) {
   using T = Tile<RT>;
@@ -135,7 +159,10 @@ __global__ void __launch_bounds__(NTHREADS, 1)
   double* sYall = reinterpret_cast<double*>(smem_raw + 1024);                  // [2][128] targets of the tile's rows (forward)
   unsigned char* sB = smem_raw + SMEM_HEADER;                                  // [STAGES][NPR][BK rows][128 bytes], swizzled
   double* sP = reinterpret_cast<double*>(sB + STAGES * STAGE_BYTES);           // [STAGES][BK][sp]
-  double* sC = sP + STAGES * BK * p.sp;                                        // [PHASES][BJ] cost-sum scratch (forward)
+  double* sC = sP + STAGES * BK * p.sp;                                        // [PHASES][BJ] cost-sum scratch (staged epilogue) /
+                                                                               // [NWARPS][BJ] per-warp cost sums (register epilogue)
+  unsigned* tile_done = released + 4;                                          // [2] warps that published their sums, by tile parity
+  volatile unsigned* combined = released + 6;                                  // tiles whose sums have been combined
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -196,6 +223,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
       mbar_init(&full[s], 1);
       released[s] = 0;
     }
+    released[4] = released[5] = released[6] = 0;
     fence_mbar_init();
   }
   fence_proxy_async();  // generic-proxy zero fill ordered before the async-proxy bulk copies
@@ -312,11 +340,21 @@ __global__ void __launch_bounds__(NTHREADS, 1)
   // one warp's epilogue overlaps the others' tensor work.  The Gaussian / identity closed form (one multiply-subtract per
   // element) is inline, every other cost functor is called four values at a time.  The epilogues that produce cost sums
   // need the tile's rows together and are staged through shared memory.
-  const bool deriv_direct = !BACKWARD && p.epilogue == PLS_EPI_COST_DERIVATIVE;
-  const bool gauss_direct = deriv_direct && p.cost.cost_id == PLS_COST_GAUSSIAN && p.cost.link_id == PLS_LINK_IDENTITY &&
-                            p.cost.closed_form != 0;
-  const bool direct = !BACKWARD && (p.epilogue == PLS_EPI_PREDICTION || deriv_direct);
-  const double inv_noise = gauss_direct ? (1.0 / p.cost.observation_noise) : 1.0;  // as cost_derivative(): gaussian.py:75-88
+  const bool deriv_direct = !BACKWARD && EPI == PLS_EPI_COST_DERIVATIVE;
+  const bool gauss_cost = p.cost.cost_id == PLS_COST_GAUSSIAN && p.cost.link_id == PLS_LINK_IDENTITY && p.cost.closed_form != 0;
+  const bool gauss_direct = deriv_direct && gauss_cost;
+  // The cost-sum epilogues (COST, and the fused derivative + cost of pls_forward_step_f64) take the register path as well when
+  // the launcher found room for the per-warp sums and a tile has at least STAGES + 1 stages (so that no warp can finish
+  // tile i + 1 before the slowest warp has finished tile i -- the copy pipeline bounds the drift to STAGES stages): every
+  // warp reduces its 8 rows per column with a shuffle reduce-scatter, publishes 256 sums, and the LAST warp of the tile adds
+  // the 8 partials in warp order (fixed order: deterministic) and writes the row tile's sums.  No block barrier.
+  const bool sums_direct = !BACKWARD && p.wbuf_ok && nchunks > STAGES &&
+                           (EPI == PLS_EPI_COST || EPI == PLS_EPI_COST_DERIVATIVE_AND_COST);
+  const bool store_direct = deriv_direct || (sums_direct && EPI == PLS_EPI_COST_DERIVATIVE_AND_COST);
+  const bool gauss_store = store_direct && gauss_cost;
+  const bool direct = !BACKWARD && (EPI == PLS_EPI_PREDICTION || deriv_direct || sums_direct);
+  const double inv_noise = gauss_cost ? (1.0 / p.cost.observation_noise) : 1.0;  // as cost_derivative(): gaussian.py:75-88
+  const double half_inv_noise = gauss_cost ? (1.0 / (2.0 * p.cost.observation_noise)) : 1.0;  // as cost_value(): gaussian.py:54-73
   const bool wide_store = ((p.ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 31u) == 0);
 
   int stage = 0;
@@ -340,7 +378,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 #pragma unroll
     for (int h = 0; h < RT; ++h) {
       const int64_t r = row0 + (warp * RT + h) * 8 + g;
-      yreg[h] = (!BACKWARD && deriv_direct && r < p.n_rows) ? p.y[r] : 0.0;
+      yreg[h] = (!BACKWARD && direct && EPI != PLS_EPI_PREDICTION && r < p.n_rows) ? p.y[r] : 0.0;
     }
 #pragma unroll
     for (int h = 0; h < RT; ++h)
@@ -440,26 +478,48 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     }
 
     if (direct) {
+      const int64_t cols_here = (p.j - j0 < BJ) ? (p.j - j0) : BJ;
+      if (sums_direct) {  // the per-warp buffer is single: the previous tile's sums must have been combined (never spins)
+        while (*combined < (unsigned)ti) {
+        }
+      }
 #pragma unroll
-      for (int h = 0; h < RT; ++h) {
-        const int64_t r = row0 + (warp * RT + h) * 8 + g;
-        if (r >= p.n_rows) continue;
-        double* orow = p.out + r * p.ldo + j0;
-        const int64_t cols_here = (p.j - j0 < BJ) ? (p.j - j0) : BJ;
+      for (int pr = 0; pr < NPR; ++pr) {
+        const int col = 16 * pr + 4 * t;
+        double cs[4] = {0.0, 0.0, 0.0, 0.0};  // cost of this thread's rows, columns col .. col + 3
 #pragma unroll
-        for (int pr = 0; pr < NPR; ++pr) {
-          const int col = 16 * pr + 4 * t;
+        for (int h = 0; h < RT; ++h) {
+          const int64_t r = row0 + (warp * RT + h) * 8 + g;
+          const bool rv = r < p.n_rows;
           double v[4] = {acc[h][2 * pr][0], acc[h][2 * pr + 1][0], acc[h][2 * pr][1], acc[h][2 * pr + 1][1]};
-          if (gauss_direct) {
+          if (sums_direct) {
+            if (gauss_cost) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const double d = v[e] - yreg[h];
+                cs[e] += rv ? half_inv_noise * (d * d) : 0.0;
+              }
+            } else {
+              const D4 c4 = cost_value4(sCost, yreg[h], D4{v[0], v[1], v[2], v[3]});
+              cs[0] += rv ? c4.a : 0.0;
+              cs[1] += rv ? c4.b : 0.0;
+              cs[2] += rv ? c4.c : 0.0;
+              cs[3] += rv ? c4.d : 0.0;
+            }
+          }
+          if (EPI == PLS_EPI_COST) continue;  // sums only
+          if (gauss_direct || gauss_store) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) v[e] = inv_noise * (v[e] - yreg[h]);
-          } else if (deriv_direct) {
+          } else if (store_direct) {
             const D4 d = cost_derivative4(sCost, sExp, yreg[h], D4{v[0], v[1], v[2], v[3]});
             v[0] = d.a;
             v[1] = d.b;
             v[2] = d.c;
             v[3] = d.d;
           }
+          if (!rv) continue;
+          double* orow = p.out + r * p.ldo + j0;
           if (col + 3 < cols_here) {
             if (wide_store) {
               asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(orow + col), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]) : "memory");
@@ -472,6 +532,39 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 #pragma unroll
             for (int e = 0; e < 4; ++e)
               if (col + e < cols_here) orow[col + e] = v[e];
+          }
+        }
+        if (sums_direct) {
+          // reduce-scatter over the 8 rows (g) of the warp: g bit 2 splits the 4 columns in halves, bit 1 picks one, bit 0
+          // completes the sum; lane (g, t) ends with column col + 2 g2 + g1 (both members of a g0 pair hold it)
+          const bool g2 = (g & 4) != 0, g1 = (g & 2) != 0;
+          double k0 = g2 ? cs[2] : cs[0], k1 = g2 ? cs[3] : cs[1];
+          k0 += __shfl_xor_sync(0xffffffffu, g2 ? cs[0] : cs[2], 16);
+          k1 += __shfl_xor_sync(0xffffffffu, g2 ? cs[1] : cs[3], 16);
+          double kk = g1 ? k1 : k0;
+          kk += __shfl_xor_sync(0xffffffffu, g1 ? k0 : k1, 8);
+          kk += __shfl_xor_sync(0xffffffffu, kk, 4);
+          if ((g & 1) == 0) sC[warp * BJ + col + (g2 ? 2 : 0) + (g1 ? 1 : 0)] = kk;
+        }
+      }
+      if (sums_direct) {
+        __syncwarp();
+        unsigned last = 0;
+        if (lane == 0) last = (atom_add_acq_rel_shared(&tile_done[ti & 1], 1u) == NWARPS - 1) ? 1u : 0u;
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last) {  // every warp has published this tile's sums: add the partials in warp order
+          double* orow = ((EPI == PLS_EPI_COST) ? p.out + rt * p.ldo : p.out2 + rt * p.ldo2) + j0;
+          for (int c = lane; c < (int)cols_here; c += 32) {
+            double v = 0.0;
+#pragma unroll
+            for (int w = 0; w < NWARPS; ++w) v += sC[w * BJ + c];
+            orow[c] = v;
+          }
+          __syncwarp();
+          if (lane == 0) {
+            tile_done[ti & 1] = 0;
+            __threadfence_block();
+            *combined = (unsigned)(ti + 1);
           }
         }
       }
@@ -498,9 +591,9 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     // a coalesced pass then applies the cost functor -- inlined once, rolled loop -- and writes whole 128-byte lines.
     const int64_t rows_here = (p.n_rows - row0 < BR) ? (p.n_rows - row0) : BR;
     const int64_t cols_here = (p.j - j0 < BJ) ? (p.j - j0) : BJ;
-    const bool dcost = (p.epilogue == PLS_EPI_COST_DERIVATIVE || p.epilogue == PLS_EPI_COST_DERIVATIVE_AND_COST);
-    const bool with_cost = (p.epilogue == PLS_EPI_COST || p.epilogue == PLS_EPI_COST_DERIVATIVE_AND_COST);
-    const bool store = (p.epilogue != PLS_EPI_COST);
+    const bool dcost = (EPI == PLS_EPI_COST_DERIVATIVE || EPI == PLS_EPI_COST_DERIVATIVE_AND_COST);
+    const bool with_cost = (EPI == PLS_EPI_COST || EPI == PLS_EPI_COST_DERIVATIVE_AND_COST);
+    const bool store = (EPI != PLS_EPI_COST);
     constexpr int PAIRS = BJ / 2;             // double2 per row
     constexpr int PHASES = NTHREADS / PAIRS;  // a thread keeps its column pair and visits rows rphase, rphase + PHASES, ...
     constexpr int PASS_ROWS = 32;
@@ -558,7 +651,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
       double v = 0.0;
 #pragma unroll
       for (int ph = 0; ph < PHASES; ++ph) v += sC[ph * BJ + tid];
-      if (p.epilogue == PLS_EPI_COST) p.out[rt * p.ldo + j0 + tid] = v;
+      if (EPI == PLS_EPI_COST) p.out[rt * p.ldo + j0 + tid] = v;
       else p.out2[rt * p.ldo2 + j0 + tid] = v;
     }
     if (tid == 0 && gc - 1 + STAGES < total_gc) {  // (staged epilogue only: the direct one never defers)
@@ -569,7 +662,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
   }
 }
 
-template <int NKD, bool BACKWARD, bool RBF, int RT>
+template <int NKD, bool BACKWARD, bool RBF, int RT, int EPI>
 cudaError_t launch_one(const pls_ctx* ctx, GenGemmParams p, cudaStream_t stream) {
   using T = Tile<RT>;
   int64_t grid = ((p.n_rows + T::BR - 1) / T::BR) * ((p.j + T::BJ - 1) / T::BJ);
@@ -582,23 +675,30 @@ cudaError_t launch_one(const pls_ctx* ctx, GenGemmParams p, cudaStream_t stream)
   }
   if (grid <= 0 || p.red_total <= 0) return cudaSuccess;
   if (grid > 2147483647LL) return cudaErrorInvalidConfiguration;
-  const size_t smem = gen_gemm_smem_bytes<RT>(p.sp);
+  size_t smem = gen_gemm_smem_bytes<RT>(p.sp);
   if ((int64_t)smem > ctx->max_smem_optin) return cudaErrorInvalidConfiguration;
+  p.wbuf_ok = 0;
+  if (!BACKWARD && (int64_t)gen_gemm_smem_bytes_wbuf<RT>(p.sp) <= ctx->max_smem_optin) {
+    if (gen_gemm_smem_bytes_wbuf<RT>(p.sp) > smem) smem = gen_gemm_smem_bytes_wbuf<RT>(p.sp);
+    p.wbuf_ok = 1;
+  }
   CUtensorMap tm3, tm2;
   cudaError_t e = make_stream_maps(ctx, p.b, p.red_total, p.ldb, T::NPR, &tm3, &tm2, &p.tma3d);
   if (e != cudaSuccess) return e;
   p.full_blocks = p.ldb / 16;
-  e = cudaFuncSetAttribute(gen_gemm_kernel<NKD, BACKWARD, RBF, RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  e = cudaFuncSetAttribute(gen_gemm_kernel<NKD, BACKWARD, RBF, RT, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  gen_gemm_kernel<NKD, BACKWARD, RBF, RT><<<(unsigned)grid, NTHREADS, smem, stream>>>(p, tm3, tm2);
+  gen_gemm_kernel<NKD, BACKWARD, RBF, RT, EPI><<<(unsigned)grid, NTHREADS, smem, stream>>>(p, tm3, tm2);
   return cudaGetLastError();
 }
 
-template <int NKD, bool BACKWARD>
-cudaError_t launch_kind(const pls_ctx* ctx, const GenGemmParams& p, cudaStream_t stream) {
+// ROLE: -1 = backward, otherwise the forward epilogue PLS_EPI_*
+template <int NKD, int ROLE>
+cudaError_t launch_role(const pls_ctx* ctx, const GenGemmParams& p, cudaStream_t stream) {
+  constexpr bool BW = ROLE < 0;
   const bool rbf = (p.kernel_id == PLS_KERNEL_RBF);
-  if (p.rt == 1) return rbf ? launch_one<NKD, BACKWARD, true, 1>(ctx, p, stream) : launch_one<NKD, BACKWARD, false, 1>(ctx, p, stream);
-  return rbf ? launch_one<NKD, BACKWARD, true, 2>(ctx, p, stream) : launch_one<NKD, BACKWARD, false, 2>(ctx, p, stream);
+  if (p.rt == 1) return rbf ? launch_one<NKD, BW, true, 1, ROLE>(ctx, p, stream) : launch_one<NKD, BW, false, 1, ROLE>(ctx, p, stream);
+  return rbf ? launch_one<NKD, BW, true, 2, ROLE>(ctx, p, stream) : launch_one<NKD, BW, false, 2, ROLE>(ctx, p, stream);
 }
 
 }  // namespace

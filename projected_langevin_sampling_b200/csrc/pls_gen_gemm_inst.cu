@@ -1,18 +1,19 @@
-// One instantiation unit of the generated-operand GEMM per exponent depth NKD = ceil((D + 2) / 4); compiled once per
-// value with -DPLS_NKD=<k> so the build can run them in parallel.
+// One instantiation unit of the generated-operand GEMM per (exponent depth NKD = ceil(D / 4), role): compiled with
+// -DPLS_NKD=<1..7> -DPLS_ROLE=<0..4> so the build can run them in parallel.  Roles 0..3 are the forward epilogues PLS_EPI_*,
+// role 4 is the backward kernel.
 #include "pls_gen_gemm.cuh"
 
-#ifndef PLS_NKD
-#error "compile with -DPLS_NKD=<1..7>"
+#if !defined(PLS_NKD) || !defined(PLS_ROLE)
+#error "compile with -DPLS_NKD=<1..7> -DPLS_ROLE=<0..4>"
 #endif
 
 namespace pls {
 
-#define PLS_CAT2(a, b) a##b
-#define PLS_CAT(a, b) PLS_CAT2(a, b)
+#define PLS_CAT4(a, b, c, d) a##b##c##d
+#define PLS_NAME(a, b, c, d) PLS_CAT4(a, b, c, d)
 
-cudaError_t PLS_CAT(launch_gen_gemm_nkd, PLS_NKD)(bool backward, const pls_ctx* ctx, const GenGemmParams& p, cudaStream_t stream) {
-  return backward ? launch_kind<PLS_NKD, true>(ctx, p, stream) : launch_kind<PLS_NKD, false>(ctx, p, stream);
+cudaError_t PLS_NAME(launch_gen_gemm_nkd, PLS_NKD, _role, PLS_ROLE)(const pls_ctx* ctx, const GenGemmParams& p, cudaStream_t stream) {
+  return launch_role<PLS_NKD, (PLS_ROLE == 4) ? -1 : PLS_ROLE>(ctx, p, stream);
 }
 
 }  // namespace pls

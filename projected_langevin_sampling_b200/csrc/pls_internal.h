@@ -36,6 +36,7 @@ struct GenGemmParams {
   int splits;    // backward role: number of reduction splits (gridDim = tiles * splits)
   int accumulate;
   int rt;  // tile shape: row tiles per warp (1: 64 x 256 CTA tile, 2: 128 x 128)
+  int wbuf_ok;          // set by the launcher: shared memory has room for the per-warp cost sums of the register epilogue
   int tma3d;            // set by the launcher: the 3-D tensor map of the streamed matrix is usable
   int64_t full_blocks;  // set by the launcher: complete 16-column blocks per row of the streamed matrix (ldb / 16)
   double* out;

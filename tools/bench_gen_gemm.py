@@ -80,7 +80,11 @@ def main():
         return best
 
     if "forward" in args.roles:
-        ms = timed(lambda: ops.forward(ctx, kid, xa, za, d, w, j, args.epilogue, out, cost=cost, y=y))
+        if args.epilogue == nat.EPI_COST_DERIVATIVE_AND_COST:
+            part = torch.zeros((n + tile_rows - 1) // tile_rows, j, dtype=torch.float64).cuda()
+            ms = timed(lambda: ops.forward_step(ctx, kid, xa, za, d, w, j, cost, y, out, part))
+        else:
+            ms = timed(lambda: ops.forward(ctx, kid, xa, za, d, w, j, args.epilogue, out, cost=cost, y=y))
         res["forward_ms"], res["forward_tflops"] = round(ms, 3), round(flops / ms / 1e9, 3)
     if "backward" in args.roles:
         ms = timed(lambda: ops.backward(ctx, kid, za, xa, d, dc, j, gp, splits, accumulate=False))
