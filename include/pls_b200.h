@@ -202,6 +202,10 @@ int pls_philox_normal_f64(pls_ctx* ctx, uint64_t seed, uint64_t step, int64_t ro
  * dense Gram and the selector.  Exposed so the tests can bound the hot loop's exponent error in ulps. */
 int pls_gram_exp_f64(pls_ctx* ctx, const double* x, int64_t n, int fast, double* out, void* stream);
 
+/* out[i] = a[i] / b[i] (op 0), log a[i] (op 1) or exp a[i] (op 2) with the BRANCH-FREE routines the register epilogue of the
+ * hot kernel uses for the cost functors (csrc/pls_cost.cuh FlatMath).  Exposed so the tests can bound their error in ulps. */
+int pls_flat_math_f64(pls_ctx* ctx, int op, const double* a, const double* b, int64_t n, double* out, void* stream);
+
 /* ---- ConditionalVariance inducing-point selector ------------------------------------------------------------- */
 /* Greedy pivoted Cholesky (src/inducing_point_selectors/conditional_variance.py:27-120) on the ALREADY PERMUTED
  * points xp_aug (augmented layout, n rows; the numpy permutation of :60 stays on the host).

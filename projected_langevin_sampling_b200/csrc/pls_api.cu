@@ -293,6 +293,12 @@ int pls_gram_exp_f64(pls_ctx* ctx, const double* x, int64_t n, int fast, double*
   return check_cuda(ctx, pls::launch_gram_exp(x, n, fast, out, (cudaStream_t)stream), "pls_gram_exp_f64");
 }
 
+int pls_flat_math_f64(pls_ctx* ctx, int op, const double* a, const double* b, int64_t n, double* out, void* stream) {
+  if (!ctx) return 1;
+  if (op < 0 || op > 2 || !a || !out || n < 0 || (op == 0 && !b)) return fail(ctx, "pls_flat_math_f64: bad arguments");
+  return check_cuda(ctx, pls::launch_flat_math(op, a, b ? b : a, n, out, (cudaStream_t)stream), "pls_flat_math_f64");
+}
+
 int64_t pls_cv_scratch_doubles(int64_t n) { return n < 0 ? 0 : pls::cv_scratch_doubles(n); }
 
 int pls_cv_select_f64(pls_ctx* ctx, int kernel_id, const double* xp_aug, int64_t n, int d, double kdiag, int m,

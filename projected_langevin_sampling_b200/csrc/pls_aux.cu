@@ -79,6 +79,22 @@ __global__ void gram_exp_kernel(const double* __restrict__ x, int64_t n, int fas
   if (i < n) out[i] = fast ? gram_exp_fast(x[i], tbl) : gram_exp(x[i]);
 }
 
+// the branch-free arithmetic of the register epilogue (FlatMath), element by element: op 0 = a / b, 1 = log a, 2 = exp a
+__global__ void flat_math_kernel(int op, const double* __restrict__ a, const double* __restrict__ b, int64_t n, double* __restrict__ out) {
+  __shared__ double tbl[64];
+  if (threadIdx.x < 64) tbl[threadIdx.x] = kExp2Table[threadIdx.x];
+  __syncthreads();
+  const FlatMath m{tbl};
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (op == 0) ? m.div(a[i], b[i]) : ((op == 1) ? m.logn(a[i]) : m.expo(a[i]));
+}
+
+cudaError_t launch_flat_math(int op, const double* a, const double* b, int64_t n, double* out, cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  flat_math_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(op, a, b, n, out);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_gram_exp(const double* x, int64_t n, int fast, double* out, cudaStream_t stream) {
   if (n <= 0) return cudaSuccess;
   gram_exp_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(x, n, fast, out);

@@ -25,6 +25,7 @@ __device__ __forceinline__ double clip(double v, double lo, double hi) { return 
 struct LibMath {
   __device__ __forceinline__ double div(double a, double b) const { return a / b; }
   __device__ __forceinline__ double expo(double x) const { return exp(x); }
+  __device__ __forceinline__ double logn(double x) const { return log(x); }
 };
 struct FlatMath {
   const double* tbl;  // 2^(j/64), j = 0..63, in shared memory
@@ -46,6 +47,38 @@ struct FlatMath {
   __device__ __forceinline__ double expo(double x) const {
     const double v = gram_exp_fast(fmin(x, 709.782712893384), tbl);
     return (x > 709.782712893384) ? __longlong_as_double(0x7ff0000000000000LL) : ((x != x) ? x : v);
+  }
+  // log x = e ln2 + 2 atanh(s), x = 2^e m with m in [sqrt(1/2), sqrt(2)), s = (m - 1) / (m + 1), |s| <= 0.1716:
+  // 2 atanh(s) = 2 s (1 + s^2/3 + ... + s^20/21) (truncation < 1e-18); m - 1 is exact, so there is no cancellation near 1.
+  // <= 2 ulp; 0 -> -inf, negative -> NaN, +inf -> +inf, NaN -> NaN by selection; denormals are rescaled by 2^54.
+  __device__ __forceinline__ double logn(double x) const {
+    const bool tiny = x < 2.2250738585072014e-308;
+    const double xs = tiny ? x * 18014398509481984.0 : x;
+    int hi = __double2hiint(xs);
+    int e = (hi >> 20) - 1023 - (tiny ? 54 : 0);
+    hi = (hi & 0x000fffff) | 0x3ff00000;  // m in [1, 2)
+    const bool upper = hi > 0x3ff6a09e;   // m > sqrt(2) (to the high word): halve it
+    hi -= upper ? 0x00100000 : 0;
+    e += upper ? 1 : 0;
+    const double m = __hiloint2double(hi, __double2loint(xs));
+    const double s = div(m - 1.0, m + 1.0);
+    const double z = s * s;
+    double q = fma(z, 1.0 / 21.0, 1.0 / 19.0);
+    q = fma(q, z, 1.0 / 17.0);
+    q = fma(q, z, 1.0 / 15.0);
+    q = fma(q, z, 1.0 / 13.0);
+    q = fma(q, z, 1.0 / 11.0);
+    q = fma(q, z, 1.0 / 9.0);
+    q = fma(q, z, 1.0 / 7.0);
+    q = fma(q, z, 1.0 / 5.0);
+    q = fma(q, z, 1.0 / 3.0);
+    const double r = 2.0 * fma(s * z, q, s);
+    const double ed = (double)e;
+    double v = fma(ed, 6.93147180369123816490e-01, fma(ed, 1.90821492927058770002e-10, r));
+    v = (x == 0.0) ? -__longlong_as_double(0x7ff0000000000000LL) : v;
+    v = (x < 0.0) ? __longlong_as_double(0x7ff8000000000000LL) : v;
+    v = (x == __longlong_as_double(0x7ff0000000000000LL)) ? x : v;
+    return (x != x) ? x : v;
   }
 };
 
@@ -84,29 +117,30 @@ __device__ __forceinline__ double link_derivative(const pls_cost& c, double f, c
 }
 
 // c(y, F) for one training point
-__device__ __forceinline__ double cost_value(const pls_cost& c, double y, double f) {
-  const double mu = link_transform(c, f);
+template <class M = LibMath>
+__device__ __forceinline__ double cost_value(const pls_cost& c, double y, double f, const M& m = M()) {
+  const double mu = link_transform(c, f, m);
   switch (c.cost_id) {
     case PLS_COST_GAUSSIAN: {
       const double e = mu - y;
-      return (1.0 / (2.0 * c.observation_noise)) * (e * e);
+      return m.div(1.0, 2.0 * c.observation_noise) * (e * e);
     }
     case PLS_COST_BERNOULLI:
-      return -log(mu) * y - log(1.0 - mu) * (1.0 - y);
+      return -m.logn(mu) * y - m.logn(1.0 - mu) * (1.0 - y);
     case PLS_COST_POISSON:
-      return -2.0 * (y * log(fabs(f))) + mu;
+      return -2.0 * (y * m.logn(fabs(f))) + mu;
     case PLS_COST_STUDENT_T: {
       const double e = mu - y;
-      return 0.5 * (c.degrees_of_freedom + 1.0) * log(1.0 + (e * e) / (c.degrees_of_freedom * (c.scale * c.scale)));
+      return 0.5 * (c.degrees_of_freedom + 1.0) * m.logn(1.0 + m.div(e * e, c.degrees_of_freedom * (c.scale * c.scale)));
     }
     case PLS_COST_MULTIMODAL: {
       const double s2 = c.observation_noise * c.observation_noise;
       const double e1 = y - mu + c.shift;
       const double e2 = y - mu;
-      const double a1 = c.log_weight_1 + (-0.5 * (e1 * e1 / s2) - c.log_normaliser);
-      const double a2 = c.log_weight_2 + (-0.5 * (e2 * e2 / s2) - c.log_normaliser);
+      const double a1 = c.log_weight_1 + (-0.5 * m.div(e1 * e1, s2) - c.log_normaliser);
+      const double a2 = c.log_weight_2 + (-0.5 * m.div(e2 * e2, s2) - c.log_normaliser);
       const double mx = fmax(a1, a2);
-      return -(mx + log(exp(a1 - mx) + exp(a2 - mx)));
+      return -(mx + m.logn(m.expo(a1 - mx) + m.expo(a2 - mx)));
     }
   }
   return 0.0;

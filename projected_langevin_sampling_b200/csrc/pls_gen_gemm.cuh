@@ -79,15 +79,31 @@ static __device__ __noinline__ D4 cost_derivative4(const pls_cost* c, const doub
   return f;
 }
 
-// Four cost VALUES per call (the energy's cost sums); log() keeps CUDA's implementation.
-static __device__ __noinline__ D4 cost_value4(const pls_cost* c, double y, D4 f) {
-  const pls_cost cc = *c;
+// Four cost VALUES per call (the energy's cost sums), specialised and branch-free like the derivatives.
+template <int CID, int LID>
+static __device__ __forceinline__ D4 cost_value4_as(const pls_cost& c, double y, const D4& f, const double* exp_table) {
+  pls_cost cc = c;
+  cc.cost_id = CID;
+  cc.link_id = LID;
+  const FlatMath m{exp_table};
   D4 r;
-  r.a = cost_value(cc, y, f.a);
-  r.b = cost_value(cc, y, f.b);
-  r.c = cost_value(cc, y, f.c);
-  r.d = cost_value(cc, y, f.d);
+  r.a = cost_value(cc, y, f.a, m);
+  r.b = cost_value(cc, y, f.b, m);
+  r.c = cost_value(cc, y, f.c, m);
+  r.d = cost_value(cc, y, f.d, m);
   return r;
+}
+static __device__ __noinline__ D4 cost_value4(const pls_cost* c, const double* exp_table, double y, D4 f) {
+  const pls_cost cc = *c;
+#define PLS_CASE(CID, LID) \
+  case (CID * 4 + LID): return cost_value4_as<CID, LID>(cc, y, f, exp_table);
+#define PLS_CASES(CID) PLS_CASE(CID, 0) PLS_CASE(CID, 1) PLS_CASE(CID, 2) PLS_CASE(CID, 3)
+  switch (cc.cost_id * 4 + cc.link_id) {
+    PLS_CASES(0) PLS_CASES(1) PLS_CASES(2) PLS_CASES(3) PLS_CASES(4)
+  }
+#undef PLS_CASES
+#undef PLS_CASE
+  return f;
 }
 
 template <int RT>
@@ -500,7 +516,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
                 cs[e] += rv ? half_inv_noise * (d * d) : 0.0;
               }
             } else {
-              const D4 c4 = cost_value4(sCost, yreg[h], D4{v[0], v[1], v[2], v[3]});
+              const D4 c4 = cost_value4(sCost, sExp, yreg[h], D4{v[0], v[1], v[2], v[3]});
               cs[0] += rv ? c4.a : 0.0;
               cs[1] += rv ? c4.b : 0.0;
               cs[2] += rv ? c4.c : 0.0;

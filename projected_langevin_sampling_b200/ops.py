@@ -184,6 +184,14 @@ def gram_exp(ctx: nat.Context, x: torch.Tensor, fast: bool) -> torch.Tensor:
     return out
 
 
+def flat_math(ctx: nat.Context, op: int, a: torch.Tensor, b: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """a / b (op 0), log a (op 1), exp a (op 2) with the register epilogue's branch-free routines (tests)."""
+    out = torch.empty_like(a)
+    ctx.check(ctx.lib.pls_flat_math_f64(ctx.handle, op, a.data_ptr(), nat.ptr(b), a.numel(), out.data_ptr(), ctx.stream()))
+    ctx.launches += 1
+    return out
+
+
 def cv_select(ctx: nat.Context, kernel_id: int, xp_aug: torch.Tensor, d: int, kdiag: float, m: int, jitter: float,
               threshold: Optional[float]) -> Tuple[torch.Tensor, int]:
     """Returns (indices into the permuted order (m,), number selected)."""

@@ -217,3 +217,37 @@ def test_row_sharded_selector_equals_unsharded(ctx, bounds, threshold):
     assert torch.equal(got_idx, want_idx)
     for s in states[1:]:  # every rank ends with the same answer
         assert torch.equal(s.indices, got_idx)
+
+
+def test_branch_free_epilogue_arithmetic_in_ulps(ctx):
+    """FlatMath (csrc/pls_cost.cuh): the division, log and exp the register epilogue evaluates without branches, against
+    float64 CPU results: <= 1 ulp (div), <= 2 ulp (log, exp); IEEE results for zero / infinite / NaN operands."""
+    from projected_langevin_sampling_b200 import ops
+
+    g = torch.Generator().manual_seed(2)
+    n = 1_000_000
+    a = (torch.randn(n, generator=g, dtype=torch.float64) * torch.exp(20 * torch.randn(n, generator=g, dtype=torch.float64)))
+    b = (torch.randn(n, generator=g, dtype=torch.float64) * torch.exp(20 * torch.randn(n, generator=g, dtype=torch.float64)))
+    q = ops.flat_math(ctx, 0, a.cuda(), b.cuda())
+    assert _ulps(q, (a / b).cuda()).max().item() <= 1.0
+    x = torch.cat([torch.exp(40 * torch.randn(n, generator=g, dtype=torch.float64)), 1.0 + 1e-3 * torch.randn(n, generator=g, dtype=torch.float64),
+                   torch.tensor([1.0, 0.5, 2.0, 2.0 ** 0.5, 0.7071067811865476, 5e-324, 1e-310, 1.7976931348623157e308])])
+    x = x[torch.isfinite(x) & (x > 0)]
+    lg = ops.flat_math(ctx, 1, x.cuda())
+    want = torch.log(x).cuda()
+    nz = want != 0
+    assert _ulps(lg[nz], want[nz]).max().item() <= 2.0
+    assert (lg[~nz] == 0).all()  # log 1 = 0 exactly
+    ex = 700 * (2 * torch.rand(n, generator=g, dtype=torch.float64) - 1)
+    assert _ulps(ops.flat_math(ctx, 2, ex.cuda()), torch.exp(ex).cuda()).max().item() <= 2.0
+    inf, nan = float("inf"), float("nan")
+    sa = torch.tensor([1.0, -1.0, 0.0, 1.0, -2.0, inf, nan, 3.0], dtype=torch.float64)
+    sb = torch.tensor([0.0, 0.0, 0.0, inf, -inf, inf, 1.0, nan], dtype=torch.float64)
+    got, want = ops.flat_math(ctx, 0, sa.cuda(), sb.cuda()).cpu(), sa / sb
+    assert torch.equal(torch.isnan(got), torch.isnan(want)) and torch.equal(got[~torch.isnan(want)], want[~torch.isnan(want)])
+    sl = torch.tensor([0.0, -1.0, inf, nan, 1.0], dtype=torch.float64)
+    got, want = ops.flat_math(ctx, 1, sl.cuda()).cpu(), torch.log(sl)
+    assert torch.equal(torch.isnan(got), torch.isnan(want)) and torch.equal(got[~torch.isnan(want)], want[~torch.isnan(want)])
+    se = torch.tensor([710.0, 1e4, inf, -1e4, nan, 0.0], dtype=torch.float64)
+    got = ops.flat_math(ctx, 2, se.cuda()).cpu()
+    assert got[0] == inf and got[1] == inf and got[2] == inf and 0 <= got[3] < 1e-300 and torch.isnan(got[4]) and got[5] == 1.0
