@@ -213,6 +213,9 @@ int pls_backward_f64(pls_ctx* ctx, int kernel_id, const double* za, int64_t m, c
   p.rows_aug = za; p.n_rows = m; p.red_aug = xa; p.red_total = n; p.b = dc; p.ldb = lddc; p.j = j;
   p.sp = pls::point_stride(d); p.d = d; p.kernel_id = kernel_id; p.epilogue = -1; p.splits = splits;
   p.accumulate = accumulate; p.out = gp; p.ldo = ldg; p.y = nullptr; p.rt = pls::choose_tile_rt(ctx, j);
+  if (n == 0 && !accumulate && m > 0)  // an empty row shard contributes a zero gradient (no kernel is launched)
+    return check_cuda(ctx, cudaMemsetAsync(gp, 0, sizeof(double) * (size_t)splits * (size_t)m * (size_t)ldg, (cudaStream_t)stream),
+                      "pls_backward_f64");
   return check_cuda(ctx, pls::launch_gen_gemm_backward(ctx, p, (cudaStream_t)stream), "pls_backward_f64");
 }
 
