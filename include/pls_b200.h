@@ -202,6 +202,12 @@ int pls_philox_normal_f64(pls_ctx* ctx, uint64_t seed, uint64_t step, int64_t ro
  * dense Gram and the selector.  Exposed so the tests can bound the hot loop's exponent error in ulps. */
 int pls_gram_exp_f64(pls_ctx* ctx, const double* x, int64_t n, int fast, double* out, void* stream);
 
+/* out = (base ? base : 0) + a x + b y + c z on (rows x j) matrices.  The particle update of the InducingPointBasis,
+ * -eta k(Z,X) Dc - eta M k(Z,Z)^{-1} P + sqrt(2 eta) e (pls/basis/inducing_point.py:140-149), from its three terms. */
+int pls_lincomb3_f64(pls_ctx* ctx, int64_t rows, int64_t j, double a, const double* x, int64_t ldx, double b, const double* y,
+                     int64_t ldy, double c, const double* z, int64_t ldz, const double* base, int64_t ldb, double* out, int64_t ldo,
+                     void* stream);
+
 /* out[i] = a[i] / b[i] (op 0), log a[i] (op 1) or exp a[i] (op 2) with the BRANCH-FREE routines the register epilogue of the
  * hot kernel uses for the cost functors (csrc/pls_cost.cuh FlatMath).  Exposed so the tests can bound their error in ulps. */
 int pls_flat_math_f64(pls_ctx* ctx, int op, const double* a, const double* b, int64_t n, double* out, void* stream);

@@ -422,11 +422,71 @@ class OrthonormalBasisOracle:
         return noise[m_k:, :] + (k_xz @ self.scaled_eigenvectors @ (particles - noise[:m_k, :]))
 
 
+class InducingPointBasisOracle:
+    """Particles are function values at the inducing points (basis/inducing_point.py:23-240).  `gpytorch.solve(input, rhs)` /
+    `solve(lhs=, input=, rhs=)` is restated as a dense solve with k(Z, Z) (gpytorch uses a Cholesky solve up to M = 800 and CG
+    above, so parity is only well-defined for M <= 800)."""
+
+    def __init__(self, base_kernel: Callable, x_induce: torch.Tensor, y_induce: torch.Tensor, x_train: torch.Tensor,
+                 r_kernel_samples: Optional[torch.Tensor] = None, additional_predictive_noise_distribution=None,
+                 r_kernel_is_base: bool = False):
+        self.base_kernel, self.x_induce, self.y_induce, self.x_train = base_kernel, x_induce, y_induce, x_train
+        self.r_kernel_samples = x_induce if r_kernel_samples is None else r_kernel_samples
+        self.additional_predictive_noise_distribution = additional_predictive_noise_distribution
+        self.r_kernel_is_base = r_kernel_is_base  # the reference tests' mock r-kernel is the plain base kernel (mockers/kernel.py:26-43)
+        self.gram_induce = self._r(x_induce, x_induce)  # :38-40
+        self.base_gram_induce = base_kernel(x_induce, x_induce)  # :41-43
+        self.base_gram_induce_train = base_kernel(x_induce, x_train)  # :44-46
+
+    def _r(self, x1, x2, extra=None):
+        if self.r_kernel_is_base:
+            return self.base_kernel(x1, x2)
+        return r_kernel(self.base_kernel, self.r_kernel_samples, x1, x2, additional_approximation_samples=extra)
+
+    @property
+    def approximation_dimension(self) -> int:  # :52-58
+        return self.x_induce.shape[0]
+
+    def initialise_particles(self, number_of_particles: int, noise_only: bool = True, seed: Optional[int] = None) -> torch.Tensor:
+        gen = torch.Generator().manual_seed(seed) if seed is not None else None
+        noise = torch.normal(mean=0.0, std=1.0, size=(self.approximation_dimension, number_of_particles), generator=gen)
+        return noise if noise_only else (self.y_induce[:, None] + noise)  # :60-80
+
+    def forward(self, particles: torch.Tensor) -> torch.Tensor:
+        """k(X, Z) k(Z, Z)^{-1} P  (:82-95)."""
+        return self.base_gram_induce_train.T @ torch.linalg.solve(self.base_gram_induce, particles)
+
+    def energy_potential(self, particles: torch.Tensor, cost: torch.Tensor) -> float:
+        """mean_j [ c_j + M/2 sum_m (k(Z,Z)^{-1} P)_mj^2 ]  (:97-119)."""
+        w = torch.linalg.solve(self.base_gram_induce, particles)
+        return (cost + self.approximation_dimension / 2 * torch.square(w).sum(dim=0)).mean().item()
+
+    def particle_update(self, particles: torch.Tensor, cost_derivative: torch.Tensor, step_size: float,
+                        noise: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """-eta k(Z,X) Dc - eta M k(Z,Z)^{-1} P + sqrt(2 eta) e,  e ~ N(0, k(Z,Z)) drawn as samplers.py:6-44 does  (:121-150).
+        `noise` injects the STANDARD normal draw z (M, J); e = V sqrt(clip(lambda, 0)) z."""
+        w = torch.linalg.solve(self.base_gram_induce, particles)
+        if noise is None:
+            e = sample_multivariate_normal(mean=torch.zeros(particles.shape[0]), cov=self.base_gram_induce, size=(particles.shape[1],)).T
+        else:
+            lam, vec = torch.linalg.eigh(self.base_gram_induce)
+            e = vec @ torch.diag(torch.sqrt(torch.clip(lam, 0, None))) @ noise
+        return (-step_size * self.base_gram_induce_train @ cost_derivative - step_size * self.approximation_dimension * w
+                + math.sqrt(2.0 * step_size) * e)
+
+    def predict_untransformed_samples(self, particles: torch.Tensor, x: torch.Tensor, noise: torch.Tensor) -> torch.Tensor:
+        """G(x) + r(x, Z) r(Z, Z)^{-1} (P - G(Z)) with the r-kernel's extra approximation samples x  (:204-240)."""
+        gram_x_induce = self._r(x, self.x_induce, extra=x)
+        gram_induce = self._r(self.x_induce, self.x_induce, extra=x)
+        m = self.approximation_dimension
+        return noise[m:, :] + gram_x_induce @ torch.linalg.solve(gram_induce, particles - noise[:m, :])
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # PLS facade -- src/projected_langevin_sampling/projected_langevin_sampling.py
 # ----------------------------------------------------------------------------------------------------------------
 class PLSOracle:
-    def __init__(self, basis: OrthonormalBasisOracle, cost: Cost):
+    def __init__(self, basis, cost: Cost):
         self.basis = basis
         self.cost = cost
 

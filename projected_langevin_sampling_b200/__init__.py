@@ -18,7 +18,7 @@ from . import kernels  # noqa: F401
 from .inducing_point_selectors import ConditionalVarianceInducingPointSelector  # noqa: F401
 from .kernels import LinearKernel, RBFKernel, ScaleKernel  # noqa: F401
 from .projected_langevin_sampling import PLS, PLSKernel  # noqa: F401
-from .projected_langevin_sampling.basis import OrthonormalBasis  # noqa: F401
+from .projected_langevin_sampling.basis import InducingPointBasis, OrthonormalBasis  # noqa: F401
 from .utils import set_seed  # noqa: F401
 
 __version__ = "0.1.0"

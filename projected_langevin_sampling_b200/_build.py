@@ -54,8 +54,22 @@ def _units():
     return units
 
 
+def _unit_hash(src: str, defs) -> str:
+    """Hash of what one object depends on: its source, every header of csrc/ and include/, the flags."""
+    h = hashlib.sha256()
+    names = sorted(f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))) + [src]
+    for name in names:
+        with open(os.path.join(CSRC, name), "rb") as f:
+            h.update(name.encode())
+            h.update(f.read())
+    with open(os.path.join(INCLUDE, "pls_b200.h"), "rb") as f:
+        h.update(f.read())
+    h.update(" ".join(NVCC_FLAGS + list(defs)).encode())
+    return h.hexdigest()
+
+
 def build_library(force: bool = False, verbose: bool = False) -> str:
-    """Compile (if sources changed) and return the path of libpls_b200.so."""
+    """Compile (if sources changed) and return the path of libpls_b200.so.  Objects are cached one by one under csrc/build/."""
     stamp = LIB + ".sha256"  # next to the library (csrc/build/ does not travel to the GPU box)
     digest = _source_hash()
     if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read().strip() == digest:
@@ -65,12 +79,18 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
 
     def compile_one(unit):
         src, defs, obj = unit
-        cmd = [nvcc, *NVCC_FLAGS, *defs, "-c", "-o", os.path.join(BUILD, obj), os.path.join(CSRC, src)]
+        out = os.path.join(BUILD, obj)
+        unit_digest = _unit_hash(src, defs)
+        if not force and not verbose and os.path.exists(out) and os.path.exists(out + ".sha256") and open(out + ".sha256").read() == unit_digest:
+            return ""
+        cmd = [nvcc, *NVCC_FLAGS, *defs, "-c", "-o", out, os.path.join(CSRC, src)]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed for {src} {defs}:\n{r.stdout}\n{r.stderr}")
+        with open(out + ".sha256", "w") as f:
+            f.write(unit_digest)
         return r.stderr
 
     units = _units()

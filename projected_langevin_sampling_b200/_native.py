@@ -82,6 +82,7 @@ SIGNATURES = {
     "pls_energy_terms_f64": (_int, [_vp, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _vp, _vp]),
     "pls_philox_normal_f64": (_int, [_vp, _u64, _u64, _i64, _i64, _i64, _vp, _i64, _vp]),
     "pls_gram_exp_f64": (_int, [_vp, _vp, _i64, _int, _vp, _vp]),
+    "pls_lincomb3_f64": (_int, [_vp, _i64, _i64, _dbl, _vp, _i64, _dbl, _vp, _i64, _dbl, _vp, _i64, _vp, _i64, _vp, _i64, _vp]),
     "pls_flat_math_f64": (_int, [_vp, _int, _vp, _vp, _i64, _vp, _vp]),
     "pls_cv_scratch_doubles": (_i64, [_i64]),
     "pls_cv_shard_scratch_doubles": (_i64, [_i64, _int, _int]),

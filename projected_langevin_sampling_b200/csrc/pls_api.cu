@@ -296,6 +296,16 @@ int pls_gram_exp_f64(pls_ctx* ctx, const double* x, int64_t n, int fast, double*
   return check_cuda(ctx, pls::launch_gram_exp(x, n, fast, out, (cudaStream_t)stream), "pls_gram_exp_f64");
 }
 
+int pls_lincomb3_f64(pls_ctx* ctx, int64_t rows, int64_t j, double a, const double* x, int64_t ldx, double b, const double* y,
+                     int64_t ldy, double c, const double* z, int64_t ldz, const double* base, int64_t ldb, double* out, int64_t ldo,
+                     void* stream) {
+  if (!ctx) return 1;
+  if (rows < 0 || j < 0 || !x || !y || !z || !out || ldx < j || ldy < j || ldz < j || ldo < j || (base && ldb < j))
+    return fail(ctx, "pls_lincomb3_f64: bad arguments");
+  return check_cuda(ctx, pls::launch_lincomb3(rows, j, a, x, ldx, b, y, ldy, c, z, ldz, base, ldb, out, ldo, (cudaStream_t)stream),
+                    "pls_lincomb3_f64");
+}
+
 int pls_flat_math_f64(pls_ctx* ctx, int op, const double* a, const double* b, int64_t n, double* out, void* stream) {
   if (!ctx) return 1;
   if (op < 0 || op > 2 || !a || !out || n < 0 || (op == 0 && !b)) return fail(ctx, "pls_flat_math_f64: bad arguments");

@@ -79,6 +79,30 @@ __global__ void gram_exp_kernel(const double* __restrict__ x, int64_t n, int fas
   if (i < n) out[i] = fast ? gram_exp_fast(x[i], tbl) : gram_exp(x[i]);
 }
 
+// out = (base ? base : 0) + a x + b y + c z on (rows x j) matrices: the InducingPointBasis update (inducing_point.py:140-149)
+__global__ void lincomb3_kernel(int64_t rows, int64_t j, double a, const double* __restrict__ x, int64_t ldx, double b,
+                                const double* __restrict__ y, int64_t ldy, double c, const double* __restrict__ z, int64_t ldz,
+                                const double* base, int64_t ldb, double* out, int64_t ldo) {
+  const int64_t col = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t r = blockIdx.y;
+  if (col >= j || r >= rows) return;
+  double v = a * x[r * ldx + col];
+  v = v + b * y[r * ldy + col];
+  v = v + c * z[r * ldz + col];
+  if (base) v = base[r * ldb + col] + v;
+  out[r * ldo + col] = v;
+}
+
+cudaError_t launch_lincomb3(int64_t rows, int64_t j, double a, const double* x, int64_t ldx, double b, const double* y, int64_t ldy,
+                            double c, const double* z, int64_t ldz, const double* base, int64_t ldb, double* out, int64_t ldo,
+                            cudaStream_t stream) {
+  if (rows <= 0 || j <= 0) return cudaSuccess;
+  if (rows > 65535) return cudaErrorInvalidConfiguration;
+  dim3 grid((unsigned)((j + 255) / 256), (unsigned)rows);
+  lincomb3_kernel<<<grid, 256, 0, stream>>>(rows, j, a, x, ldx, b, y, ldy, c, z, ldz, base, ldb, out, ldo);
+  return cudaGetLastError();
+}
+
 // the branch-free arithmetic of the register epilogue (FlatMath), element by element: op 0 = a / b, 1 = log a, 2 = exp a
 __global__ void flat_math_kernel(int op, const double* __restrict__ a, const double* __restrict__ b, int64_t n, double* __restrict__ out) {
   __shared__ double tbl[64];

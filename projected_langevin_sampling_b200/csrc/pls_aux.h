@@ -49,6 +49,9 @@ cudaError_t launch_energy_terms(const double* partial, int64_t tiles, int64_t ld
                                 int64_t m_k, const double* inv_lambda, int64_t j, double* out, cudaStream_t stream);
 
 cudaError_t launch_advance_counter(uint64_t* counter, uint64_t increment, cudaStream_t stream);
+cudaError_t launch_lincomb3(int64_t rows, int64_t j, double a, const double* x, int64_t ldx, double b, const double* y, int64_t ldy,
+                            double c, const double* z, int64_t ldz, const double* base, int64_t ldb, double* out, int64_t ldo,
+                            cudaStream_t stream);
 cudaError_t launch_flat_math(int op, const double* a, const double* b, int64_t n, double* out, cudaStream_t stream);
 cudaError_t launch_gram_exp(const double* x, int64_t n, int fast, double* out, cudaStream_t stream);
 

@@ -30,11 +30,13 @@ ROW_ALIGN = 128
 class LangevinEngine:
     def __init__(self, ctx: nat.Context, kernel_id: int, d: int, xa: torch.Tensor, za: torch.Tensor, vt: torch.Tensor,
                  inv_lambda: torch.Tensor, j: int, dc_budget_bytes: int = DEFAULT_DC_BUDGET,
-                 gradient_reduce: Optional[Callable[[torch.Tensor], None]] = None):
+                 gradient_reduce: Optional[Callable[[torch.Tensor], None]] = None,
+                 weights_fn: Optional[Callable[[torch.Tensor, torch.Tensor], None]] = None):
         self.ctx, self.kernel_id, self.d = ctx, kernel_id, d
         self.xa, self.za, self.vt, self.inv_lambda = xa, za, vt, inv_lambda
         self.n, self.m, self.m_k, self.j = xa.shape[0], za.shape[0], vt.shape[1], j
         self.gradient_reduce = gradient_reduce
+        self.weights_fn = weights_fn  # fills W (M x J) from the particles; default W = V~ P (OrthonormalBasis)
         dev = xa.device
         self.ldj = ops.even(j)
         rows = max(ROW_ALIGN, (dc_budget_bytes // (self.ldj * 8)) // ROW_ALIGN * ROW_ALIGN)
@@ -51,6 +53,9 @@ class LangevinEngine:
 
     # ---- pieces ------------------------------------------------------------------------------------------------------
     def _weights(self, particles: torch.Tensor) -> torch.Tensor:
+        if self.weights_fn is not None:
+            self.weights_fn(particles, self.w)  # e.g. W = k(Z, Z)^{-1} P for the InducingPointBasis
+            return self.w
         return ops.gemm(self.ctx, self.vt, particles, self.w)  # W = V~ P
 
     def gradient(self, particles: torch.Tensor, cost: nat.PlsCost, y: torch.Tensor, with_cost: bool = False) -> torch.Tensor:

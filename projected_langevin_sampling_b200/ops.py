@@ -184,6 +184,16 @@ def gram_exp(ctx: nat.Context, x: torch.Tensor, fast: bool) -> torch.Tensor:
     return out
 
 
+def lincomb3(ctx: nat.Context, a: float, x: torch.Tensor, b: float, y: torch.Tensor, c: float, z: torch.Tensor, j: int,
+             out: torch.Tensor, base: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[:, :j] = (base[:, :j] if base is given) + a x + b y + c z."""
+    ctx.check(ctx.lib.pls_lincomb3_f64(ctx.handle, x.shape[0], j, float(a), x.data_ptr(), _ld(x), float(b), y.data_ptr(), _ld(y),
+                                       float(c), z.data_ptr(), _ld(z), nat.ptr(base), _ld(base) if base is not None else 0,
+                                       out.data_ptr(), _ld(out), ctx.stream()))
+    ctx.launches += 1
+    return out
+
+
 def flat_math(ctx: nat.Context, op: int, a: torch.Tensor, b: Optional[torch.Tensor] = None) -> torch.Tensor:
     """a / b (op 0), log a (op 1), exp a (op 2) with the register epilogue's branch-free routines (tests)."""
     out = torch.empty_like(a)

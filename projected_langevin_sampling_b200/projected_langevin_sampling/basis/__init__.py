@@ -1,4 +1,5 @@
 from .base import PLSBasis
+from .inducing_point import InducingPointBasis
 from .orthonormal import OrthonormalBasis
 
-__all__ = ["OrthonormalBasis", "PLSBasis"]
+__all__ = ["InducingPointBasis", "OrthonormalBasis", "PLSBasis"]

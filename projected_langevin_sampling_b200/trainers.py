@@ -31,7 +31,22 @@ def train_pls(pls: PLS, particles: torch.Tensor, number_of_epochs: int, step_siz
     del tqdm_desc
     basis, cost = pls.basis, pls.cost
     if not pls._fused():
-        raise TypeError("train_pls needs an OrthonormalBasis and a cost with a CUDA implementation (there is no CPU fallback)")
+        raise TypeError("train_pls needs a basis and a cost with a CUDA implementation (there is no CPU fallback)")
+    if not hasattr(basis, "scaled_eigenvectors"):  # InducingPointBasis: the reference-shaped loop (update, then energy)
+        if philox_seed is not None:
+            raise ValueError("philox_seed needs an OrthonormalBasis")
+        p = basis._particles(particles)
+        energy_potentials: List[float] = []
+        early_stopper = EarlyStopper(patience=early_stopper_patience)
+        for _ in range(number_of_epochs):
+            basis.fused_particle_update(p, cost, float(step_size), in_place=True)
+            energy = pls.calculate_energy_potential(p)
+            if early_stopper.should_stop(loss=energy, step_size=float(step_size)):
+                break
+            energy_potentials.append(energy)
+        if p is not particles:
+            particles.copy_(p.to(device=particles.device, dtype=particles.dtype))
+        return particles, energy_potentials
     p = basis._particles(particles)  # float64, on the device, unit column stride (a copy if `particles` is not)
     assert (
         p.shape[0] == basis.approximation_dimension

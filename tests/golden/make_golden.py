@@ -178,7 +178,34 @@ def train_loop_runs():
     np.savez(os.path.join(HERE, "train_loop_runs.npz"), **out)
 
 
+def ipb_runs():
+    """The reference's InducingPointBasis (basis/inducing_point.py): forward, cost derivative, energy and one Langevin update
+    on a small, well-conditioned ARD problem (k(Z, Z) is solved by Cholesky on both sides)."""
+    from src.projected_langevin_sampling.basis import InducingPointBasis  # noqa: E402
+
+    g = torch.Generator().manual_seed(41)
+    n, d, m, j = 70, 2, 7, 5
+    x = torch.randn(n, d, generator=g)
+    z = torch.tensor([[-1.5, -1.0], [-0.7, 1.2], [0.0, 0.0], [0.8, -1.3], [1.6, 0.9], [-1.8, 1.9], [2.2, -0.4]])
+    ls = torch.tensor([0.9, 1.1])
+    kernel = make_kernel(ls, 1.3, ard=d)
+    y = torch.sin(x.sum(1)) + 0.1 * torch.randn(n, generator=g)
+    y_induce = torch.sin(z.sum(1))
+    basis = InducingPointBasis(kernel=PLSKernel(base_kernel=kernel, approximation_samples=z), x_induce=z, y_induce=y_induce, x_train=x)
+    pls = PLS(basis=basis, cost=GaussianCost(observation_noise=0.3, y_train=y, link_function=IdentityLinkFunction()))
+    p_noise = pls.initialise_particles(number_of_particles=j, seed=5)
+    p = pls.initialise_particles(number_of_particles=j, seed=5, noise_only=False)
+    torch.manual_seed(17)
+    delta = pls.calculate_particle_update(p, 1e-3)
+    np.savez(os.path.join(HERE, "ipb_runs.npz"), x=x.numpy(), z=z.numpy(), y=y.numpy(), y_induce=y_induce.numpy(), lengthscale=ls.numpy(),
+             outputscale=1.3, observation_noise=0.3, p_noise=p_noise.numpy(), p=p.numpy(),
+             f=basis.calculate_untransformed_train_prediction_samples(p).numpy(), dc=pls.calculate_cost_derivative(p).numpy(),
+             cost=pls.calculate_cost(p).numpy(), energy=pls.calculate_energy_potential(p), delta=delta.numpy(), step_size=1e-3,
+             noise_seed=17, cond=float(torch.linalg.cond(basis.base_gram_induce)))
+    print("ipb: cond(k(Z,Z)) =", float(torch.linalg.cond(basis.base_gram_induce)), "energy", pls.calculate_energy_potential(p))
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["readme_demo", "one_step_all_costs", "selector_runs", "train_loop_runs"]
+    which = sys.argv[1:] or ["readme_demo", "one_step_all_costs", "selector_runs", "train_loop_runs", "ipb_runs"]
     for name in which:
         globals()[name]()

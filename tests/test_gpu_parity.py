@@ -633,3 +633,80 @@ def test_step_size_search_runner_and_checkpoint(b200, tmp_path):
         assert torch.equal(p2, got_p) and lr2 == got_lr and n2 == got_n and pls2.observation_noise == 0.25
     finally:
         torch.set_default_dtype(torch.float32)
+
+
+# ---- InducingPointBasis ("next" row) ---------------------------------------------------------------------------------------
+def test_ipb_reference_vectors(b200):  # reference tests/test_basis.py:98-116,248-269,369-387,495-519 (linear mock kernel)
+    y2 = torch.tensor([2.1, 3.3])
+    f_want = torch.tensor([[1.2656511068, -0.8267806172, -2.1464431286], [-6.1349906921, -5.1450047493, 4.8272337914],
+                           [-8.9970912933, -5.7714910507, 8.1600494385], [1.5409765244, -0.2934455872, -2.1787719727],
+                           [0.5684509277, -1.0845184326, -1.3986053467]])
+    basis = b200.InducingPointBasis(b200.PLSKernel(b200.LinearKernel(), Z2), Z2, y2, X5)
+    assert basis.approximation_dimension == 2
+    assert torch.allclose(basis.initialise_particles(3, seed=0).cpu().float(), P23)
+    assert torch.allclose(basis.initialise_particles(3, seed=0, noise_only=False).cpu().float(), y2[:, None] + P23)
+    assert torch.allclose(basis.calculate_untransformed_train_prediction_samples(P23).cpu().float(), f_want, rtol=1e-3, atol=1e-3)
+    assert np.isclose(basis.calculate_energy_potential(P23, torch.ones(3)), 275.2294006347656, rtol=1e-3)
+
+
+def test_ipb_against_reference_run(b200, golden_dir):
+    """The CUDA InducingPointBasis against a run of the reference's own class (tests/golden/make_golden.py ipb_runs):
+    forward, cost derivative, cost, energy and one Langevin update with the reference's noise stream replayed."""
+    torch.set_default_dtype(torch.float64)
+    try:
+        costs, links = _costs_mod()
+        g = np.load(os.path.join(golden_dir, "ipb_runs.npz"))
+        x, z, y = torch.from_numpy(g["x"]), torch.from_numpy(g["z"]), torch.from_numpy(g["y"])
+        kernel = b200.ScaleKernel(b200.RBFKernel(ard_num_dims=2, lengthscale=torch.from_numpy(g["lengthscale"])), outputscale=float(g["outputscale"]))
+        basis = b200.InducingPointBasis(b200.PLSKernel(kernel, z), z, torch.from_numpy(g["y_induce"]), x)
+        pls = b200.PLS(basis, costs.GaussianCost(float(g["observation_noise"]), y, links.IdentityLinkFunction()))
+        p = pls.initialise_particles(number_of_particles=5, seed=5, noise_only=False)
+        assert rel_err(p, torch.from_numpy(g["p"])) < 1e-14
+        assert rel_err(basis.calculate_untransformed_train_prediction_samples(p), torch.from_numpy(g["f"])) < TOL
+        assert rel_err(pls.calculate_cost_derivative(p), torch.from_numpy(g["dc"])) < TOL
+        assert rel_err(pls.calculate_cost(p), torch.from_numpy(g["cost"])) < TOL
+        assert abs(pls.calculate_energy_potential(p) - float(g["energy"])) <= TOL * abs(float(g["energy"]))
+        torch.manual_seed(int(g["noise_seed"]))
+        assert rel_err(pls.calculate_particle_update(p, float(g["step_size"])), torch.from_numpy(g["delta"])) < TOL
+        # the unfused composition (materialised cost derivative) gives the same update
+        torch.manual_seed(int(g["noise_seed"]))
+        dc = pls.cost.calculate_cost_derivative(basis.calculate_untransformed_train_prediction_samples(p))
+        assert rel_err(basis.calculate_particle_update(p, dc, float(g["step_size"])), torch.from_numpy(g["delta"])) < TOL
+    finally:
+        torch.set_default_dtype(torch.float32)
+
+
+def test_ipb_step_matches_oracle_at_size(b200):
+    """InducingPointBasis at a size with several row tiles and Dc chunks, against the oracle (well-separated inducing points
+    keep k(Z, Z) well conditioned, so the two Cholesky solves agree far below the tolerance)."""
+    from oracle.pls_oracle import InducingPointBasisOracle
+
+    torch.set_default_dtype(torch.float64)
+    try:
+        costs, links = _costs_mod()
+        g = torch.Generator().manual_seed(51)
+        n, d, m, j = 1500, 2, 36, 70
+        x = 4 * torch.rand(n, d, generator=g, dtype=torch.float64) - 2
+        gx, gy = torch.meshgrid(torch.linspace(-2, 2, 6), torch.linspace(-2, 2, 6), indexing="ij")
+        z = torch.stack([gx.reshape(-1), gy.reshape(-1)], dim=1).double()
+        ls = torch.tensor([0.5, 0.6], dtype=torch.float64)
+        y = torch.sin(x.sum(1)) + 0.1 * torch.randn(n, generator=g, dtype=torch.float64)
+        y_induce = torch.sin(z.sum(1))
+        orc_basis = InducingPointBasisOracle(RBFScaleKernel(ls, 1.1), z, y_induce, x)
+        assert torch.linalg.cond(orc_basis.base_gram_induce) < 1e3
+        orc = PLSOracle(orc_basis, Cost("student_t", y, Link("identity"), degrees_of_freedom=5.0, scale=0.8))
+        kernel = b200.ScaleKernel(b200.RBFKernel(ard_num_dims=d, lengthscale=ls), outputscale=1.1)
+        basis = b200.InducingPointBasis(b200.PLSKernel(kernel, z), z, y_induce, x, dc_budget_bytes=512 * 70 * 8)
+        pls = b200.PLS(basis, costs.StudentTCost(5.0, y, links.IdentityLinkFunction(), scale=0.8))
+        p = y_induce[:, None] + 0.3 * torch.randn(m, j, generator=g, dtype=torch.float64)
+        zn = torch.randn(m, j, generator=g, dtype=torch.float64)
+        want = orc.calculate_particle_update(p, 2e-3, noise=zn)
+        assert rel_err(pls.calculate_particle_update(p.cuda(), 2e-3, noise=zn), want) < TOL
+        assert len(basis.engine(j).chunks) > 1
+        e_want = orc.calculate_energy_potential(p)
+        assert abs(pls.calculate_energy_potential(p.cuda()) - e_want) <= TOL * abs(e_want)
+        q = p.cuda().clone()
+        basis.fused_particle_update(q, pls.cost, 2e-3, noise=zn, in_place=True)
+        assert rel_err(q, p + want) < TOL
+    finally:
+        torch.set_default_dtype(torch.float32)

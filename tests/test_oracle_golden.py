@@ -309,3 +309,57 @@ def test_train_loop_against_reference_run(name, kind, golden_dir):
         assert (p - want_p).abs().max().item() <= 1e-10 * want_p.abs().max().item()
     finally:
         torch.set_default_dtype(torch.float32)
+
+
+# ---- InducingPointBasis ("next" row): reference tests/test_basis.py:74-115,191-269,331-387,456-519 + a reference run ------
+Y2 = torch.tensor([2.1, 3.3])
+F53_IPB = torch.tensor(
+    [
+        [1.2656511068, -0.8267806172, -2.1464431286],
+        [-6.1349906921, -5.1450047493, 4.8272337914],
+        [-8.9970912933, -5.7714910507, 8.1600494385],
+        [1.5409765244, -0.2934455872, -2.1787719727],
+        [0.5684509277, -1.0845184326, -1.3986053467],
+    ]
+)
+
+
+def ipb():
+    from oracle.pls_oracle import InducingPointBasisOracle
+
+    return InducingPointBasisOracle(LinearKernel(), Z2.double(), Y2.double(), X5.double(), r_kernel_is_base=True)
+
+
+def test_ipb_reference_vectors():
+    b = ipb()
+    assert b.approximation_dimension == 2  # tests/test_basis.py:98-116
+    assert torch.allclose(b.initialise_particles(3, seed=0).float(), P23)  # :248-269 (noise only)
+    assert torch.allclose(b.initialise_particles(3, seed=0, noise_only=False).float(), Y2[:, None] + P23)
+    # the 2 x 2 linear Gram has condition number ~1e4: float32 golden values, float64 here
+    assert torch.allclose(b.forward(P23.double()).float(), F53_IPB, rtol=1e-3, atol=1e-3)  # :369-387
+    assert np.isclose(b.energy_potential(P23.double(), torch.ones(3, dtype=torch.float64)), 275.2294006347656, rtol=1e-3)  # :495-519
+
+
+def test_ipb_against_reference_run(golden_dir):
+    from oracle.pls_oracle import InducingPointBasisOracle
+
+    torch.set_default_dtype(torch.float64)
+    try:
+        g = np.load(os.path.join(golden_dir, "ipb_runs.npz"))
+        x, z, y = torch.from_numpy(g["x"]), torch.from_numpy(g["z"]), torch.from_numpy(g["y"])
+        basis = InducingPointBasisOracle(RBFScaleKernel(torch.from_numpy(g["lengthscale"]), float(g["outputscale"])), z,
+                                         torch.from_numpy(g["y_induce"]), x)
+        pls = PLSOracle(basis, Cost("gaussian", y, Link("identity"), observation_noise=float(g["observation_noise"])))
+        assert torch.equal(basis.initialise_particles(5, seed=5), torch.from_numpy(g["p_noise"]))
+        p = basis.initialise_particles(5, seed=5, noise_only=False)
+        assert torch.allclose(p, torch.from_numpy(g["p"]), rtol=1e-14)
+        tol = 1e-10
+        rel = lambda a, b: (a - b).abs().max().item() / b.abs().max().item()  # noqa: E731
+        assert rel(basis.forward(p), torch.from_numpy(g["f"])) < tol
+        assert rel(pls.calculate_cost_derivative(p), torch.from_numpy(g["dc"])) < tol
+        assert rel(pls.calculate_cost(p), torch.from_numpy(g["cost"])) < tol
+        assert abs(pls.calculate_energy_potential(p) - float(g["energy"])) < tol * abs(float(g["energy"]))
+        torch.manual_seed(int(g["noise_seed"]))
+        assert rel(pls.calculate_particle_update(p, float(g["step_size"])), torch.from_numpy(g["delta"])) < tol
+    finally:
+        torch.set_default_dtype(torch.float32)
