@@ -14,7 +14,11 @@ def sample_multivariate_normal(mean: torch.Tensor, cov: torch.Tensor, size: Opti
                                seed: Optional[int] = None) -> torch.Tensor:
     generator = torch.Generator().manual_seed(seed) if seed is not None else None
     size = (1,) if not size else size
-    eigenvalues, eigenvectors = torch.linalg.eigh(cov)
+    # The decomposition runs on the HOST (LAPACK) whatever the device of `cov`: eigenvector signs (and bases of repeated
+    # eigenvalues) differ between LAPACK and cuSOLVER, and the draw V sqrt(lambda) z depends on them -- the reference's runs
+    # and golden vectors are CPU ones.  These matrices are (M_k + N*) x (M_k + N*): predict-time sizes.
+    eigenvalues, eigenvectors = torch.linalg.eigh(cov.detach().cpu())
+    eigenvalues, eigenvectors = eigenvalues.to(cov.device), eigenvectors.to(cov.device)
     eigenvalues = torch.clip(eigenvalues, 0, None)
     normal_sample = torch.normal(mean=0.0, std=1.0, size=(eigenvalues.shape[0], *size), generator=generator)
     dev = eigenvectors.device

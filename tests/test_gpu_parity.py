@@ -710,3 +710,31 @@ def test_ipb_step_matches_oracle_at_size(b200):
         assert rel_err(q, p + want) < TOL
     finally:
         torch.set_default_dtype(torch.float32)
+
+
+def _mock_r_kernel(pkg, samples):
+    """The reference tests' MockProjectedLangevinSamplingKernel (mockers/kernel.py:26-43): its forward is the base kernel."""
+    from projected_langevin_sampling_b200.kernels import dense_gram
+
+    class MockPLSKernel(pkg.PLSKernel):
+        def forward(self, x1, x2, additional_approximation_samples=None, **kw):
+            return dense_gram(self.base_kernel, x1, x2)
+
+    return MockPLSKernel(pkg.LinearKernel(), samples)
+
+
+def test_reference_predictive_noise_vectors(b200):
+    """sample_predictive_noise of both bases against the reference's golden draws (tests/test_basis.py:522-635 ONB, :640-838
+    IPB; seed 0, float32 default dtype as in the reference's test run) and IPB predict with the noise given (:862-1010)."""
+    xs = torch.tensor([[3.0, 2.0, 3.2], [1.5, 6.5, 1.5]])
+    onb_want = torch.tensor([[0.0851, -0.1569, -0.2067], [3.1662, 4.6236, -1.2954], [1.3697, 1.4171, 0.7368], [3.9759, 6.4164, -2.9854]])
+    ipb_want = torch.tensor([[1.4442, 3.7593, -0.4158], [1.9489, 4.2264, -0.9286], [3.0377, 3.1129, -3.4442], [1.4840, 1.3103, 0.6729]])
+    onb = b200.OrthonormalBasis(_mock_r_kernel(b200, Z2), Z2, X5, verbose=False)
+    b200.set_seed(0)
+    assert torch.allclose(onb.sample_predictive_noise(P23, xs).cpu().float(), onb_want, rtol=1e-3, atol=2e-4)
+    ipb = b200.InducingPointBasis(_mock_r_kernel(b200, Z2), Z2, torch.tensor([2.1, 3.3]), X5)
+    b200.set_seed(0)
+    # rank-deficient 4 x 4 covariance: the round-off eigenvalue of the float32 golden run contributes ~1e-3 of noise
+    assert torch.allclose(ipb.sample_predictive_noise(P23, xs).cpu().float(), ipb_want, rtol=1e-3, atol=1e-2)
+    pred = ipb.predict_untransformed_samples(P23, xs, noise=ipb_want)
+    assert torch.allclose(pred.cpu().float(), torch.tensor([[-4.4373, -3.6672, 2.9305], [-7.8718, -6.6582, 8.8616]]), rtol=2e-3, atol=2e-3)

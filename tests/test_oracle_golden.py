@@ -363,3 +363,19 @@ def test_ipb_against_reference_run(golden_dir):
         assert rel(pls.calculate_particle_update(p, float(g["step_size"])), torch.from_numpy(g["delta"])) < tol
     finally:
         torch.set_default_dtype(torch.float32)
+
+
+def test_ipb_predictive_noise_and_predict_reference_vectors():
+    """reference tests/test_basis.py:640-838 (predictive noise, seed 0, no extra distribution) and :862-1010 (predict with the
+    noise given); the reference builds the basis with its mock r-kernel = the plain linear kernel."""
+    xs = torch.tensor([[3.0, 2.0, 3.2], [1.5, 6.5, 1.5]])
+    noise_want = torch.tensor([[1.4442, 3.7593, -0.4158], [1.9489, 4.2264, -0.9286], [3.0377, 3.1129, -3.4442], [1.4840, 1.3103, 0.6729]])
+    k = LinearKernel()
+    cov = torch.cat([torch.cat([k(Z2, Z2), k(Z2, xs)], 1), torch.cat([k(Z2, xs).T, k(xs, xs)], 1)], 0)
+    set_seed(0)
+    got = sample_multivariate_normal(torch.zeros(4), cov, size=(3,)).T
+    # the 4 x 4 linear Gram of 3-D points has rank 3: its fourth eigenvalue is float32 round-off (~1e-6) and contributes
+    # sqrt(1e-6) ~ 1e-3 of noise that depends on how the matrix was assembled, hence the absolute tolerance
+    assert torch.allclose(got, noise_want, rtol=1e-3, atol=1e-2)
+    pred = ipb().predict_untransformed_samples(P23.double(), xs.double(), noise_want.double())
+    assert torch.allclose(pred.float(), torch.tensor([[-4.4373, -3.6672, 2.9305], [-7.8718, -6.6582, 8.8616]]), rtol=2e-3, atol=2e-3)
