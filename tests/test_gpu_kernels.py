@@ -251,3 +251,66 @@ def test_branch_free_epilogue_arithmetic_in_ulps(ctx):
     se = torch.tensor([710.0, 1e4, inf, -1e4, nan, 0.0], dtype=torch.float64)
     got = ops.flat_math(ctx, 2, se.cuda()).cpu()
     assert got[0] == inf and got[1] == inf and got[2] == inf and 0 <= got[3] < 1e-300 and torch.isnan(got[4]) and got[5] == 1.0
+
+
+def _random_shapes(count, seed):
+    rng = np.random.default_rng(seed)
+    shapes = []
+    for _ in range(count):
+        n = int(rng.integers(1, 1400))
+        m = int(rng.integers(2, 420))
+        d = int(rng.integers(1, 27))
+        j = int(rng.integers(1, 700))
+        pad = int(rng.choice([0, 2, 6, 14]))
+        shapes.append((n, m, d, j, j + (j & 1) + pad))
+    return shapes
+
+
+@pytest.mark.parametrize("n,m,d,j,ld", _random_shapes(14, seed=2024))
+def test_generated_operand_gemm_random_shapes(ctx, n, m, d, j, ld):
+    """Seeded random (N, M, D, J, leading dimension) draws -- ragged tiles, every exponent depth, one- and many-stage
+    reductions, persistent CTAs with zero, one or several tiles: all four forward epilogues and the backward role against
+    dense float64 torch algebra on pls_gram_f64's matrix."""
+    from projected_langevin_sampling_b200 import _native as nat, ops
+
+    g = torch.Generator().manual_seed(n * 7919 + m * 31 + j)
+    x = torch.randn(n, d, generator=g, dtype=torch.float64).cuda()
+    z = torch.randn(m, d, generator=g, dtype=torch.float64).cuda()
+    inv_ls = [1.0 / (2.0 + d ** 0.5 + 0.05 * k) for k in range(d)]
+    centre = z.mean(0).tolist()
+    xa = ops.prepare_points(ctx, nat.KERNEL_RBF, x, inv_ls, centre, 0.0)
+    za = ops.prepare_points(ctx, nat.KERNEL_RBF, z, inv_ls, centre, float(np.log(1.4)))
+    k_xz = ops.gram(ctx, nat.KERNEL_RBF, xa, za, d)
+    w = torch.randn(m, ld, generator=g, dtype=torch.float64).cuda()
+    y = torch.randn(n, generator=g, dtype=torch.float64).cuda()
+    want_f = k_xz @ w[:, :j]
+    scale = max(1.0, want_f.abs().max().item())
+    cost = nat.PlsCost()
+    cost.cost_id, cost.link_id, cost.closed_form = nat.COST_STUDENT_T, nat.LINK_IDENTITY, 1
+    cost.degrees_of_freedom, cost.scale, cost.link_jitter, cost.probit_divisor = 4.0, 0.7, 1e-10, 2.0 ** 0.5
+    e = want_f - y[:, None]
+    want_dc = 5.0 * e / (4.0 * 0.49 + e * e)
+    want_c = (2.5 * torch.log(1.0 + e * e / (4.0 * 0.49))).sum(0)
+    f = torch.full((n, ld), 3.0, dtype=torch.float64).cuda()
+    ops.forward(ctx, nat.KERNEL_RBF, xa, za, d, w, j, nat.EPI_PREDICTION, f)
+    assert (f[:, :j] - want_f).abs().max().item() < 1e-12 * scale and (f[:, j:] == 3.0).all()
+    dc = torch.full((n, ld), 3.0, dtype=torch.float64).cuda()
+    ops.forward(ctx, nat.KERNEL_RBF, xa, za, d, w, j, nat.EPI_COST_DERIVATIVE, dc, cost=cost, y=y)
+    assert (dc[:, :j] - want_dc).abs().max().item() < 1e-11 * max(1.0, want_dc.abs().max().item()) and (dc[:, j:] == 3.0).all()
+    tiles = (n + ops.forward_tile_rows(ctx, j) - 1) // ops.forward_tile_rows(ctx, j)
+    part = torch.zeros(tiles, ld, dtype=torch.float64).cuda()
+    ops.forward(ctx, nat.KERNEL_RBF, xa, za, d, w, j, nat.EPI_COST, part, cost=cost, y=y)
+    assert (part[:, :j].sum(0) - want_c).abs().max().item() < 1e-11 * max(1.0, want_c.abs().max().item())
+    dc2 = torch.full((n, ld), 4.0, dtype=torch.float64).cuda()
+    part2 = torch.zeros(tiles, ld, dtype=torch.float64).cuda()
+    ops.forward_step(ctx, nat.KERNEL_RBF, xa, za, d, w, j, cost, y, dc2, part2)
+    assert (dc2[:, :j] - want_dc).abs().max().item() < 1e-11 * max(1.0, want_dc.abs().max().item()) and (dc2[:, j:] == 4.0).all()
+    assert (part2[:, :j].sum(0) - want_c).abs().max().item() < 1e-11 * max(1.0, want_c.abs().max().item())
+    dcin = torch.randn(n, ld, generator=g, dtype=torch.float64).cuda()
+    want_g = k_xz.T @ dcin[:, :j]
+    splits = ops.backward_splits(ctx, n, m, j)
+    gp = torch.full((splits, m, ld), -2.0, dtype=torch.float64).cuda()
+    ops.backward(ctx, nat.KERNEL_RBF, za, xa, d, dcin, j, gp, splits, accumulate=False)
+    out = torch.empty(m, ld, dtype=torch.float64).cuda()
+    ops.reduce_splits(ctx, gp, j, out)
+    assert (out[:, :j] - want_g).abs().max().item() < 1e-11 * max(1.0, want_g.abs().max().item()) and (gp[:, :, j:] == -2.0).all()
