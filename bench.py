@@ -212,6 +212,51 @@ def run_reference_arm(args, workload):
     emit(line)
 
 
+# ---- library bar: the reference's formulation on the same GPU with library kernels ------------------------------------------
+def library_bar_sample(workload: dict, pls, eta: float, steps: int = 3):
+    """SURVEY.md section 8(d) "library bar": the reference's own step algebra (orthonormal.py:98-108,151-158) run on this GPU
+    with torch fp64 matmul (cuBLAS DGEMM) and the dense Gram of a bounded row block cached on the device -- what moving the
+    reference to CUDA unchanged would give.  A 65 536-row block at full M and J is timed with CUDA events and scaled
+    linearly to N.  Reported beside the headline; nothing of it runs inside the timed region."""
+    from projected_langevin_sampling_b200 import _native as nat, ops
+
+    ctx = nat.context()
+    basis = pls.basis
+    n_full, j = workload["n"], workload["j"]
+    n_s = min(n_full, 65536)
+    eng = basis.engine(j)
+    k_xz = ops.gram(ctx, eng.kernel_id, eng.xa[:n_s], eng.za, eng.d)  # (N_s, M) dense, cached like the reference's K_zx
+    k_zx = k_xz.T.contiguous()
+    vt, lam = basis.scaled_eigenvectors, basis.eigenvalues
+    y = pls.cost.y_device()[:n_s]
+    p = torch.randn(vt.shape[1], j, dtype=torch.float64, device=vt.device)
+    xi = torch.randn_like(p)
+
+    def step():
+        f = (k_xz @ vt) @ p  # left to right as the reference writes it
+        if workload["cost"] == "gaussian":
+            dc = (1 / 0.01) * (f - y[:, None])
+        elif workload["cost"] == "bernoulli":
+            pr = torch.clip(torch.sigmoid(f), 1e-10, 1 - 1e-10)
+            dc = -y[:, None] * (1 - pr) + (1 - y[:, None]) * pr
+        else:
+            dc = -2 * y[:, None] / f + 2 * f
+        return ((-eta * vt.T) @ k_zx) @ dc - eta * torch.diag(torch.reciprocal(lam)) @ p + math.sqrt(2 * eta) * xi
+
+    step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps * (n_full / n_s)
+    return {"value": j / (ms * 1e-3), "unit": UNIT, "ms_per_step_extrapolated": ms,
+            "what": (f"reference algebra on this GPU with torch fp64 matmul (cuBLAS DGEMM), dense Gram cached, rows {n_s}/{n_full} at full "
+                     f"M={workload['m']}, J={j}, scaled linearly to N (noise pre-drawn on the device)")}
+
+
 # ---- FP64 peak -----------------------------------------------------------------------------------------------------------
 def measure_fp64_peak(n: int = 8192, reps: int = 6) -> float:
     """cuBLAS DGEMM n^3 via torch.matmul, best of `reps` (TFLOP/s): the FP64 denominator MEASURED_PEAKS.json lacks."""
@@ -491,6 +536,12 @@ def main():
     if not args.no_cpu_baseline:
         r = cpu_reference_sample(workload, steps=2, warmup=1)
         cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    library_bar = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            library_bar = library_bar_sample(workload, pls, eta)
+        except torch.OutOfMemoryError as exc:  # a reported comparison, never a reason to lose the line
+            library_bar = {"unavailable": str(exc).splitlines()[0]}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, min_warmup),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if grid is not None else "weak", "vs_baseline": None, "dtype": "f64",
@@ -502,6 +553,7 @@ def main():
                    "l2": "per-step working set (Dc chunk 8 GiB written+read) exceeds the 126 MB L2; no flush needed",
                    "particles_finite": finite, "setup_s": setup_s},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+        "library_bar": library_bar,
     }
     emit(line)
     if dist is not None:
