@@ -1,3 +1,6 @@
+"""Numerical study for DESIGN.md section 8.5: FP64 GEMM emulated with radix-256 integer digit products (the arithmetic an int8
+tcgen05 path would run): error against an 80-bit reference on a C4-like ill-conditioned K(X,Z) * (V~ P), for several digit counts.
+CPU only (numpy); not part of the product or the tests."""
 import numpy as np, math, time
 rng = np.random.default_rng(0)
 n, d, m, j = 2048, 8, 1024, 32
