@@ -138,10 +138,10 @@ __device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint
   c[3] = n3;
 }
 
-// standard normal for element (row, global column) of step `step`; both members of a column pair share one Philox
-// block, so the stream does not depend on how the particle axis is sharded or tiled.
-__device__ __forceinline__ double philox_normal(uint64_t seed, uint64_t step, int64_t row, int64_t gcol) {
-  uint32_t c[4] = {(uint32_t)row, (uint32_t)(gcol >> 1), (uint32_t)step, (uint32_t)(step >> 32) ^ (uint32_t)((uint64_t)row >> 32)};
+// standard normals for the column pair (2 * pair, 2 * pair + 1) of `row` at step `step`: one Philox block and one
+// Box-Muller transform give both, so the stream does not depend on how the particle axis is sharded or tiled.
+__device__ __forceinline__ void philox_normal_pair(uint64_t seed, uint64_t step, int64_t row, int64_t pair, double& even, double& odd) {
+  uint32_t c[4] = {(uint32_t)row, (uint32_t)pair, (uint32_t)step, (uint32_t)(step >> 32) ^ (uint32_t)((uint64_t)row >> 32)};
   uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
 #pragma unroll
   for (int r = 0; r < 10; ++r) {
@@ -156,7 +156,15 @@ __device__ __forceinline__ double philox_normal(uint64_t seed, uint64_t step, in
   const double rad = sqrt(-2.0 * log(u1));
   double sn, cs;
   sincospi(2.0 * u2, &sn, &cs);
-  return (gcol & 1) ? rad * sn : rad * cs;
+  even = rad * cs;
+  odd = rad * sn;
+}
+
+// standard normal for element (row, global column)
+__device__ __forceinline__ double philox_normal(uint64_t seed, uint64_t step, int64_t row, int64_t gcol) {
+  double even, odd;
+  philox_normal_pair(seed, step, row, gcol >> 1, even, odd);
+  return (gcol & 1) ? odd : even;
 }
 
 __global__ void philox_fill_kernel(uint64_t seed, uint64_t step, int64_t rows, int64_t j, int64_t joff, double* out,
@@ -233,23 +241,36 @@ __global__ void __launch_bounds__(128) small_gemm_kernel(const SmallGemmParams p
 
   const double sq2eta = sqrt(2.0 * p.eta);
   const uint64_t step = (UPDATE && p.step_counter) ? p.step + *p.step_counter : p.step;
+  // a small grid is launched gridDim.z times over: every copy forms the (cheap) product, copy z finishes row group mt == z,
+  // which spreads the noise generation of the update epilogue over more SMs
+  const int zsel = (gridDim.z > 1) ? (int)blockIdx.z : -1;
 #pragma unroll
   for (int mt = 0; mt < 4; ++mt) {
     const int64_t r = row0 + wm * 32 + mt * 8 + g;
-    if (r >= p.rows) continue;
+    if (r >= p.rows || (zsel >= 0 && zsel != mt)) continue;
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) {
+      const int64_t cpair = col0 + wn * 32 + nt * 8 + 2 * t;  // this thread's two adjacent columns
+      double xi2[2] = {0.0, 0.0};
+      if (UPDATE && p.noise_mode == PLS_NOISE_PHILOX && cpair < p.j) {
+        const int64_t gc = p.j_global_offset + cpair;
+        if ((gc & 1) == 0) {  // the two columns are one Philox pair
+          philox_normal_pair(p.seed, step, r, gc >> 1, xi2[0], xi2[1]);
+        } else {
+          xi2[0] = philox_normal(p.seed, step, r, gc);
+          xi2[1] = philox_normal(p.seed, step, r, gc + 1);
+        }
+      }
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        const int64_t c = col0 + wn * 32 + nt * 8 + 2 * t + e;
+        const int64_t c = cpair + e;
         if (c >= p.j) continue;
         double v = acc[mt][nt][e];
         if (UPDATE) {
           // delta = -eta * (V~^T k(Z,X) Dc) - eta * (1/lambda) P + sqrt(2 eta) xi      orthonormal.py:151-158
           const double pv = p.particles[r * p.ldp + c];
-          double xi = 0.0;
+          double xi = xi2[e];
           if (p.noise_mode == PLS_NOISE_GIVEN) xi = p.xi[r * p.ldxi + c];
-          else if (p.noise_mode == PLS_NOISE_PHILOX) xi = philox_normal(p.seed, step, r, p.j_global_offset + c);
           double delta = -p.eta * v - p.eta * (p.inv_lambda[r] * pv);
           delta = delta + sq2eta * xi;
           v = p.in_place ? (pv + delta) : delta;
@@ -271,6 +292,7 @@ cudaError_t launch_small_gemm(const SmallGemmParams& p, bool trans_a, bool updat
   if (p.rows <= 0 || p.j <= 0) return cudaSuccess;
   dim3 grid((unsigned)((p.j + GT - 1) / GT), (unsigned)((p.rows + GT - 1) / GT));
   if (grid.y > 65535) return cudaErrorInvalidConfiguration;
+  if (update && p.noise_mode == PLS_NOISE_PHILOX && (uint64_t)grid.x * grid.y <= 148) grid.z = 4;  // see the epilogue
   if (trans_a) {
     if (update) small_gemm_kernel<true, true><<<grid, 128, 0, stream>>>(p);
     else small_gemm_kernel<true, false><<<grid, 128, 0, stream>>>(p);

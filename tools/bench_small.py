@@ -25,16 +25,23 @@ def main():
     p = pls.initialise_particles(w["j"], seed=1)
     eta = 1e-6
     out = {"workload": w["label"], "steps": args.steps}
-    for mode in ("eager", "cuda_graph"):
-        q = p.clone()
-        pls.run(q, eta, 5, seed=1, cuda_graph=(mode == "cuda_graph"))
+    def timed(q, steps, graph):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        pls.run(q, eta, args.steps, seed=1, cuda_graph=(mode == "cuda_graph"))
+        pls.run(q, eta, steps, seed=1, cuda_graph=graph)
         torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
+        return time.perf_counter() - t0
+
+    for mode in ("eager", "cuda_graph"):
+        graph = mode == "cuda_graph"
+        q = p.clone()
+        timed(q, 5, graph)
+        # marginal cost of a step: a graph-mode call also pays one capture + instantiation, which the difference removes
+        short, long_ = timed(q, args.steps // 10, graph), timed(q, args.steps + args.steps // 10, graph)
+        dt = long_ - short
         out[mode] = {"us_per_step": round(dt / args.steps * 1e6, 1), "particle_updates_per_s": round(w["j"] * args.steps / dt, 1),
-                     "step_tflops": round(4.0 * w["n"] * w["m"] * w["j"] * args.steps / dt * 1e-12, 2)}
+                     "step_tflops": round(4.0 * w["n"] * w["m"] * w["j"] * args.steps / dt * 1e-12, 2),
+                     "call_overhead_ms": round((short - dt / args.steps * (args.steps // 10)) * 1e3, 2)}
     print(json.dumps(out))
 
 
