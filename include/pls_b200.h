@@ -158,6 +158,26 @@ int pls_backward_f64(pls_ctx* ctx, int kernel_id, const double* za, int64_t m, c
                      const double* dc, int64_t lddc, int64_t j, double* gp, int64_t ldg, int splits, int accumulate,
                      void* stream);
 
+/* ---- the same contractions with the Gram kept resident in HBM ----------------------------------------------------
+ * The reference holds k(Z, X) as a (lazy) tensor for the whole run (pls/basis/orthonormal.py:36-41,104-108,151-155).  When
+ * n x m doubles fit in device memory the caller may do the same: k = k(X, Z) from pls_gram_f64, row-major,
+ *   ldk = pls_gram_cache_ld(m) (m rounded up to 128), readable for pls_gram_cache_rows(n) rows (n rounded up to 128;
+ *   the padding -- columns [m, ldk) and the rows past n -- is read and multiplied by zeros: it MUST be finite),
+ * and the three entry points below run the contraction kernels with their Gram values LOADED (one streaming 8-byte read
+ * per value and tile) instead of generated, which takes the exponent DMMAs and the exp off the FP64 pipe.  `k` may point
+ * at any row of a larger cache (row chunks).  Arguments and results are otherwise those of pls_forward_f64,
+ * pls_forward_step_f64 and pls_backward_f64 (equal to round-off: pls_gram_f64's values and the kernels' generated ones are
+ * two evaluations of the same exponent, each within an ulp). */
+int64_t pls_gram_cache_ld(int64_t m);
+int64_t pls_gram_cache_rows(int64_t n);
+int pls_forward_cached_f64(pls_ctx* ctx, const double* k, int64_t ldk, int64_t n, int64_t m, const double* w, int64_t ldw,
+                           int64_t j, int epilogue, const pls_cost* cost, const double* y, double* out, int64_t ldo, void* stream);
+int pls_forward_step_cached_f64(pls_ctx* ctx, const double* k, int64_t ldk, int64_t n, int64_t m, const double* w, int64_t ldw,
+                                int64_t j, const pls_cost* cost, const double* y, double* dc, int64_t lddc, double* cost_partial,
+                                int64_t ldcp, void* stream);
+int pls_backward_cached_f64(pls_ctx* ctx, const double* k, int64_t ldk, int64_t m, int64_t n, const double* dc, int64_t lddc,
+                            int64_t j, double* gp, int64_t ldg, int splits, int accumulate, void* stream);
+
 /* out[r][c] = sum_s gp[s][r][c] in increasing s (deterministic). */
 int pls_reduce_splits_f64(pls_ctx* ctx, const double* gp, int splits, int64_t rows, int64_t j, int64_t ldg,
                           double* out, int64_t ldo, void* stream);

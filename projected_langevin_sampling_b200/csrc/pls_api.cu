@@ -158,65 +158,104 @@ int pls_gemm_f64(pls_ctx* ctx, int trans_a, const double* a, int64_t lda, const 
   return check_cuda(ctx, pls::launch_small_gemm(p, trans_a != 0, false, (cudaStream_t)stream), "pls_gemm_f64");
 }
 
-int pls_forward_f64(pls_ctx* ctx, int kernel_id, const double* xa, int64_t n, const double* za, int64_t m, int d,
-                    const double* w, int64_t ldw, int64_t j, int epilogue, const pls_cost* cost, const double* y,
-                    double* out, int64_t ldo, void* stream) {
+// Checks of a cached Gram argument (pls_*_cached_f64): k is (rows x ldk), ldk = pls_gram_cache_ld(m)
+static int check_gram(pls_ctx* ctx, const char* who, const double* k, int64_t ldk, int64_t m) {
+  if (!k || !aligned16(k)) return fail(ctx, "%s: the cached Gram must be a 16-byte aligned device pointer", who);
+  if (ldk != pls_gram_cache_ld(m)) return fail(ctx, "%s: ldk must be pls_gram_cache_ld(m) = %lld", who, (long long)pls_gram_cache_ld(m));
+  return 0;
+}
+
+static int forward_common(pls_ctx* ctx, const char* who, int kernel_id, const double* xa, int64_t n, const double* za, int64_t m,
+                          int d, const double* gram, int64_t ldk, const double* w, int64_t ldw, int64_t j, int epilogue,
+                          const pls_cost* cost, const double* y, double* out, int64_t ldo, double* out2, int64_t ldo2, void* stream) {
   if (!ctx) return 1;
-  if (check_kernel(ctx, kernel_id, d)) return 1;
-  if (epilogue < PLS_EPI_PREDICTION || epilogue > PLS_EPI_COST) return fail(ctx, "pls_forward_f64: unknown epilogue %d", epilogue);
-  if (n < 0 || m < 0 || j < 0 || !xa || !za || !w || !out) return fail(ctx, "pls_forward_f64: bad arguments");
-  if (ldw < j || (ldw & 1) || !aligned16(w)) return fail(ctx, "pls_forward_f64: w must be 16-byte aligned with an even ldw >= j");
-  if (ldo < j) return fail(ctx, "pls_forward_f64: ldo < j");
-  if (epilogue != PLS_EPI_COST && ((ldo & 1) || !aligned16(out)))
-    return fail(ctx, "pls_forward_f64: out must be 16-byte aligned with an even ldo");
+  if (!gram && check_kernel(ctx, kernel_id, d)) return 1;
+  if (epilogue < PLS_EPI_PREDICTION || epilogue > PLS_EPI_COST_DERIVATIVE_AND_COST) return fail(ctx, "%s: unknown epilogue %d", who, epilogue);
+  if (n < 0 || m < 0 || j < 0 || !w || !out || (!gram && (!xa || !za))) return fail(ctx, "%s: bad arguments", who);
+  if (gram && check_gram(ctx, who, gram, ldk, m)) return 1;
+  if (ldw < j || (ldw & 1) || !aligned16(w)) return fail(ctx, "%s: w must be 16-byte aligned with an even ldw >= j", who);
+  if (ldo < j) return fail(ctx, "%s: ldo < j", who);
+  if (epilogue != PLS_EPI_COST && ((ldo & 1) || !aligned16(out))) return fail(ctx, "%s: out must be 16-byte aligned with an even ldo", who);
+  if (epilogue == PLS_EPI_COST_DERIVATIVE_AND_COST && (!out2 || ldo2 < j)) return fail(ctx, "%s: bad cost-sum output", who);
   pls::GenGemmParams p{};
   if (epilogue != PLS_EPI_PREDICTION) {
     if (check_cost(ctx, cost)) return 1;
-    if (!y) return fail(ctx, "pls_forward_f64: y is NULL");
+    if (!y) return fail(ctx, "%s: y is NULL", who);
     p.cost = *cost;
   }
   p.rows_aug = xa; p.n_rows = n; p.red_aug = za; p.red_total = m; p.b = w; p.ldb = ldw; p.j = j;
+  p.gram = gram; p.ldk = ldk;
   p.sp = pls::point_stride(d); p.d = d; p.kernel_id = kernel_id; p.epilogue = epilogue; p.splits = 1; p.accumulate = 0;
   p.rt = pls::choose_tile_rt(ctx, j);
-  p.out = out; p.ldo = ldo; p.y = y;
-  return check_cuda(ctx, pls::launch_gen_gemm_forward(ctx, p, (cudaStream_t)stream), "pls_forward_f64");
+  p.out = out; p.ldo = ldo; p.out2 = out2; p.ldo2 = ldo2; p.y = y;
+  return check_cuda(ctx, pls::launch_gen_gemm_forward(ctx, p, (cudaStream_t)stream), who);
+}
+
+int64_t pls_gram_cache_ld(int64_t m) { return m <= 0 ? 128 : (m + 127) / 128 * 128; }
+int64_t pls_gram_cache_rows(int64_t n) { return n <= 0 ? 128 : (n + 127) / 128 * 128; }
+
+int pls_forward_f64(pls_ctx* ctx, int kernel_id, const double* xa, int64_t n, const double* za, int64_t m, int d,
+                    const double* w, int64_t ldw, int64_t j, int epilogue, const pls_cost* cost, const double* y,
+                    double* out, int64_t ldo, void* stream) {
+  if (ctx && epilogue == PLS_EPI_COST_DERIVATIVE_AND_COST) return fail(ctx, "pls_forward_f64: unknown epilogue %d", epilogue);
+  return forward_common(ctx, "pls_forward_f64", kernel_id, xa, n, za, m, d, nullptr, 0, w, ldw, j, epilogue, cost, y, out, ldo,
+                        nullptr, 0, stream);
+}
+
+int pls_forward_cached_f64(pls_ctx* ctx, const double* k, int64_t ldk, int64_t n, int64_t m, const double* w, int64_t ldw,
+                           int64_t j, int epilogue, const pls_cost* cost, const double* y, double* out, int64_t ldo, void* stream) {
+  if (ctx && epilogue == PLS_EPI_COST_DERIVATIVE_AND_COST) return fail(ctx, "pls_forward_cached_f64: unknown epilogue %d", epilogue);
+  if (ctx && !k) return fail(ctx, "pls_forward_cached_f64: k is NULL");
+  return forward_common(ctx, "pls_forward_cached_f64", PLS_KERNEL_RBF, nullptr, n, nullptr, m, 1, k, ldk, w, ldw, j, epilogue, cost, y,
+                        out, ldo, nullptr, 0, stream);
 }
 
 int pls_forward_step_f64(pls_ctx* ctx, int kernel_id, const double* xa, int64_t n, const double* za, int64_t m, int d,
                          const double* w, int64_t ldw, int64_t j, const pls_cost* cost, const double* y, double* dc,
                          int64_t lddc, double* cost_partial, int64_t ldcp, void* stream) {
+  if (ctx && (!dc || !cost_partial || !y)) return fail(ctx, "pls_forward_step_f64: bad arguments");
+  return forward_common(ctx, "pls_forward_step_f64", kernel_id, xa, n, za, m, d, nullptr, 0, w, ldw, j, PLS_EPI_COST_DERIVATIVE_AND_COST,
+                        cost, y, dc, lddc, cost_partial, ldcp, stream);
+}
+
+int pls_forward_step_cached_f64(pls_ctx* ctx, const double* k, int64_t ldk, int64_t n, int64_t m, const double* w, int64_t ldw,
+                                int64_t j, const pls_cost* cost, const double* y, double* dc, int64_t lddc, double* cost_partial,
+                                int64_t ldcp, void* stream) {
+  if (ctx && (!k || !dc || !cost_partial || !y)) return fail(ctx, "pls_forward_step_cached_f64: bad arguments");
+  return forward_common(ctx, "pls_forward_step_cached_f64", PLS_KERNEL_RBF, nullptr, n, nullptr, m, 1, k, ldk, w, ldw, j,
+                        PLS_EPI_COST_DERIVATIVE_AND_COST, cost, y, dc, lddc, cost_partial, ldcp, stream);
+}
+
+static int backward_common(pls_ctx* ctx, const char* who, int kernel_id, const double* za, int64_t m, const double* xa, int64_t n,
+                           int d, const double* gram, int64_t ldk, const double* dc, int64_t lddc, int64_t j, double* gp, int64_t ldg,
+                           int splits, int accumulate, void* stream) {
   if (!ctx) return 1;
-  if (check_kernel(ctx, kernel_id, d)) return 1;
-  if (n < 0 || m < 0 || j < 0 || !xa || !za || !w || !dc || !cost_partial || !y) return fail(ctx, "pls_forward_step_f64: bad arguments");
-  if (ldw < j || (ldw & 1) || !aligned16(w)) return fail(ctx, "pls_forward_step_f64: w must be 16-byte aligned with an even ldw >= j");
-  if (lddc < j || (lddc & 1) || !aligned16(dc)) return fail(ctx, "pls_forward_step_f64: dc must be 16-byte aligned with an even lddc >= j");
-  if (ldcp < j) return fail(ctx, "pls_forward_step_f64: ldcp < j");
-  if (check_cost(ctx, cost)) return 1;
+  if (!gram && check_kernel(ctx, kernel_id, d)) return 1;
+  if (n < 0 || m < 0 || j < 0 || !dc || !gp || splits < 1 || (!gram && (!xa || !za))) return fail(ctx, "%s: bad arguments", who);
+  if (gram && check_gram(ctx, who, gram, ldk, m)) return 1;
+  if (lddc < j || (lddc & 1) || !aligned16(dc)) return fail(ctx, "%s: dc must be 16-byte aligned with an even lddc >= j", who);
+  if (ldg < j || (ldg & 1) || !aligned16(gp)) return fail(ctx, "%s: gp must be 16-byte aligned with an even ldg >= j", who);
   pls::GenGemmParams p{};
-  p.cost = *cost;
-  p.rows_aug = xa; p.n_rows = n; p.red_aug = za; p.red_total = m; p.b = w; p.ldb = ldw; p.j = j;
-  p.sp = pls::point_stride(d); p.d = d; p.kernel_id = kernel_id; p.epilogue = PLS_EPI_COST_DERIVATIVE_AND_COST; p.splits = 1;
-  p.accumulate = 0; p.rt = pls::choose_tile_rt(ctx, j);
-  p.out = dc; p.ldo = lddc; p.out2 = cost_partial; p.ldo2 = ldcp; p.y = y;
-  return check_cuda(ctx, pls::launch_gen_gemm_forward(ctx, p, (cudaStream_t)stream), "pls_forward_step_f64");
+  p.rows_aug = za; p.n_rows = m; p.red_aug = xa; p.red_total = n; p.b = dc; p.ldb = lddc; p.j = j;
+  p.gram = gram; p.ldk = ldk;
+  p.sp = pls::point_stride(d); p.d = d; p.kernel_id = kernel_id; p.epilogue = -1; p.splits = splits;
+  p.accumulate = accumulate; p.out = gp; p.ldo = ldg; p.y = nullptr; p.rt = pls::choose_tile_rt(ctx, j);
+  if (n == 0 && !accumulate && m > 0)  // an empty row shard contributes a zero gradient (no kernel is launched)
+    return check_cuda(ctx, cudaMemsetAsync(gp, 0, sizeof(double) * (size_t)splits * (size_t)m * (size_t)ldg, (cudaStream_t)stream), who);
+  return check_cuda(ctx, pls::launch_gen_gemm_backward(ctx, p, (cudaStream_t)stream), who);
 }
 
 int pls_backward_f64(pls_ctx* ctx, int kernel_id, const double* za, int64_t m, const double* xa, int64_t n, int d,
                      const double* dc, int64_t lddc, int64_t j, double* gp, int64_t ldg, int splits, int accumulate,
                      void* stream) {
-  if (!ctx) return 1;
-  if (check_kernel(ctx, kernel_id, d)) return 1;
-  if (n < 0 || m < 0 || j < 0 || !xa || !za || !dc || !gp || splits < 1) return fail(ctx, "pls_backward_f64: bad arguments");
-  if (lddc < j || (lddc & 1) || !aligned16(dc)) return fail(ctx, "pls_backward_f64: dc must be 16-byte aligned with an even lddc >= j");
-  if (ldg < j || (ldg & 1) || !aligned16(gp)) return fail(ctx, "pls_backward_f64: gp must be 16-byte aligned with an even ldg >= j");
-  pls::GenGemmParams p{};
-  p.rows_aug = za; p.n_rows = m; p.red_aug = xa; p.red_total = n; p.b = dc; p.ldb = lddc; p.j = j;
-  p.sp = pls::point_stride(d); p.d = d; p.kernel_id = kernel_id; p.epilogue = -1; p.splits = splits;
-  p.accumulate = accumulate; p.out = gp; p.ldo = ldg; p.y = nullptr; p.rt = pls::choose_tile_rt(ctx, j);
-  if (n == 0 && !accumulate && m > 0)  // an empty row shard contributes a zero gradient (no kernel is launched)
-    return check_cuda(ctx, cudaMemsetAsync(gp, 0, sizeof(double) * (size_t)splits * (size_t)m * (size_t)ldg, (cudaStream_t)stream),
-                      "pls_backward_f64");
-  return check_cuda(ctx, pls::launch_gen_gemm_backward(ctx, p, (cudaStream_t)stream), "pls_backward_f64");
+  return backward_common(ctx, "pls_backward_f64", kernel_id, za, m, xa, n, d, nullptr, 0, dc, lddc, j, gp, ldg, splits, accumulate, stream);
+}
+
+int pls_backward_cached_f64(pls_ctx* ctx, const double* k, int64_t ldk, int64_t m, int64_t n, const double* dc, int64_t lddc,
+                            int64_t j, double* gp, int64_t ldg, int splits, int accumulate, void* stream) {
+  if (ctx && !k) return fail(ctx, "pls_backward_cached_f64: k is NULL");
+  return backward_common(ctx, "pls_backward_cached_f64", PLS_KERNEL_RBF, nullptr, m, nullptr, n, 1, k, ldk, dc, lddc, j, gp, ldg, splits,
+                         accumulate, stream);
 }
 
 int pls_reduce_splits_f64(pls_ctx* ctx, const double* gp, int splits, int64_t rows, int64_t j, int64_t ldg, double* out,

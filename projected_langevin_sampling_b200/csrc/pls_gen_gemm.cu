@@ -66,7 +66,7 @@ static const Launcher kLaunchers[MAX_NKD][5] = {PLS_ROW(1), PLS_ROW(2), PLS_ROW(
 // role: 0..3 = forward epilogue PLS_EPI_*, 4 = backward
 static cudaError_t dispatch(int role, const pls_ctx* ctx, const GenGemmParams& p, cudaStream_t stream) {
   if ((p.rt != 1 && p.rt != 2) || role < 0 || role > 4) return cudaErrorInvalidValue;
-  const int nkd = point_ksteps(p.d);
+  const int nkd = p.gram ? 1 : point_ksteps(p.d);
   if (nkd < 1 || nkd > MAX_NKD) return cudaErrorInvalidValue;
   return kLaunchers[nkd - 1][role](ctx, p, stream);
 }

@@ -145,6 +145,20 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, in
                "l"(tm), "r"(c0), "r"(c1), "r"(smem_u32(bar))
                : "memory");
 }
+constexpr int KSRC_LINEAR = 0, KSRC_RBF = 1, KSRC_CACHED = 2;
+
+// streaming read-only loads of cached Gram values (each value is used once per tile: keep it out of L1)
+__device__ __forceinline__ double2 ldg_stream_v2(const double* ptr) {
+  double2 v;
+  asm("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(ptr));
+  return v;
+}
+__device__ __forceinline__ double ldg_stream(const double* ptr) {
+  double v;
+  asm("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(ptr));
+  return v;
+}
+
 __device__ __forceinline__ unsigned atom_add_acq_rel_shared(unsigned* addr, unsigned v) {
   unsigned old;
   asm volatile("atom.acq_rel.cta.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(addr)), "r"(v) : "memory");
@@ -159,9 +173,12 @@ __device__ __forceinline__ unsigned atom_add_shared(unsigned* addr, unsigned v) 
   return old;
 }
 
+// KSRC: where the Gram values come from -- generated from the augmented points (KSRC_RBF: exponent DMMAs + exp, KSRC_LINEAR:
+// exponent DMMAs only) or read from a Gram matrix the caller keeps in HBM (KSRC_CACHED: p.gram, rows = training points,
+// columns = inducing points; no exponent work at all on the FP64 pipe, one streaming load per value instead).
 // EPI: the forward epilogue (PLS_EPI_*), a template parameter so that every kernel carries only its own epilogue's code and
 // register budget; the backward role is instantiated with EPI = -1.
-template <int NKD, bool BACKWARD, bool RBF, int RT, int EPI>
+template <int NKD, bool BACKWARD, int KSRC, int RT, int EPI>
 __global__ void __launch_bounds__(NTHREADS, 1)
     gen_gemm_kernel(const GenGemmParams p, const __grid_constant__ CUtensorMap tm3, const __grid_constant__ CUtensorMap tm2) {
   using T = Tile<RT>;
@@ -267,7 +284,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 #pragma unroll 1
       for (int blk = 0; blk < NPR; ++blk) tma_load_2d(dst + blk * BLOCK_BYTES, &tm2, (int)j0 + 16 * blk, (int)k0, bar);
     }
-    bulk_g2s(sP + stage * BK * sp, p.red_aug + k0 * sp, (uint32_t)(kc * sp * 8), bar);
+    if (KSRC != KSRC_CACHED) bulk_g2s(sP + stage * BK * sp, p.red_aug + k0 * sp, (uint32_t)(kc * sp * 8), bar);  // (sp = 0 when cached)
   };
   if (tid == 0) {
     for (int gc = 0; gc < STAGES && gc < total_gc; ++gc) issue(gc);
@@ -278,6 +295,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
   double a2[RT][NKD];
   double crow[RT];
   auto load_rows = [&](int64_t row0, double (&a)[RT][NKD], double (&cr)[RT]) {
+    if (KSRC == KSRC_CACHED) return;
 #pragma unroll
     for (int h = 0; h < RT; ++h) {
       const int64_t r = row0 + (warp * RT + h) * 8 + g;
@@ -311,7 +329,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     }
   };
   auto gram_value = [&](double sv, bool valid) {
-    const double v = RBF ? gram_exp_fast(sv, sExp) : sv;
+    const double v = (KSRC == KSRC_RBF) ? gram_exp_fast(sv, sExp) : sv;
     return valid ? v : 0.0;
   };
   // one k4 step: brow = this lane's 16-byte chunk of its reduction row in column block 0
@@ -338,7 +356,33 @@ __global__ void __launch_bounds__(NTHREADS, 1)
   constexpr int NBLK = GROUPS / LA;
   // Gram values of groups [g0, g0 + LA) of the point tile Pt; `first` = this thread's first reduction point of group g0,
   // counted from `begin` (points past the end of the reduction give 0)
+  const double* kbase[RT];  // cached Gram: this thread's row (forward) / column (backward) of the tile, set per tile
   auto gram_block = [&](const double* Pt, int g0, int first, double (&k)[LA][2][RT]) {
+    if (KSRC == KSRC_CACHED) {
+      // points first + 8 q and first + 8 q + 1 (from `begin`) of each of this thread's rows: forward = two adjacent columns of a
+      // Gram row (one 16-byte load), backward = the same column of two adjacent Gram rows.  The loads are issued a block ahead
+      // of the DMMAs that consume them, like the generated values.
+#pragma unroll
+      for (int q = 0; q < LA; ++q) {
+        const int64_t pt = begin + first + 8 * q;
+#pragma unroll
+        for (int h = 0; h < RT; ++h) {
+          double2 v;
+          if (BACKWARD) {
+            v.x = ldg_stream(kbase[h] + pt * p.ldk);
+            v.y = ldg_stream(kbase[h] + (pt + 1) * p.ldk);
+          } else {
+            v = ldg_stream_v2(kbase[h] + pt);
+          }
+          // no masking: a point past the end of the reduction meets a zero row of the streamed matrix (the tensor map
+          // zero-fills rows outside it), and the cache's padding is finite by contract.  A select here would be the first use
+          // of the load and stall the warp for the whole memory latency before the block's DMMAs (measured: 9 % of the samples).
+          k[q][0][h] = v.x;
+          k[q][1][h] = v.y;
+        }
+      }
+      return;
+    }
 #pragma unroll
     for (int q = 0; q < LA; ++q) {
       double s[RT][2];
@@ -404,15 +448,26 @@ __global__ void __launch_bounds__(NTHREADS, 1)
         acc[h][nt][1] = 0.0;
       }
 
-    double kc[LA][2][RT];  // Gram values of the block being multiplied
+    if (KSRC == KSRC_CACHED) {
+#pragma unroll
+      for (int h = 0; h < RT; ++h) {
+        const int64_t r = row0 + (warp * RT + h) * 8 + g;  // rows past n_rows are readable padding (see pls_b200.h)
+        kbase[h] = BACKWARD ? p.gram + r : p.gram + r * p.ldk;
+      }
+    }
+    // Gram values of the block being multiplied and of the next one, in two register sets that swap roles block by block.
+    // No set is ever copied into the other: the only readers of a freshly produced (cached mode: freshly LOADED) set are the
+    // DMMAs of the following block, a whole block of tensor work later, so the load latency hides behind it.  (With a
+    // kc = kn copy ptxas hoists each move to right after the last DMMA that reads its target, ~30 DMMAs after the load.)
+    double kA[LA][2][RT], kB[LA][2][RT];
     if (nchunks > 0) {
       mbar_wait(&full[stage], phase);
-      gram_block(sP + stage * BK * sp, 0, 2 * t, kc);
+      gram_block(sP + stage * BK * sp, 0, 2 * t, kA);
     }
-#pragma unroll 1
-    for (int c = 0; c < nchunks; ++c, ++gc) {
-      // One iteration = one 32-point stage = 4 groups, fully unrolled (264 DMMAs).  The next stage was issued two chunk
-      // times ago; its Gram values (same tile only: they depend on the tile's rows) are formed before this stage's DMMAs.
+    // One chunk = one 32-point stage = 4 groups, fully unrolled (264 DMMAs).  The next stage was issued two chunk times ago;
+    // its Gram values (same tile only: they depend on the tile's rows) are formed before this stage's last block of DMMAs.
+    // k0 holds the chunk's first block on entry; the chunk's successor block ends up in k1 (NBLK odd) or k0 (NBLK even).
+    auto run_chunk = [&](int c, double (&k0)[LA][2][RT], double (&k1)[LA][2][RT]) {
       const int nstage = (stage + 1 == STAGES) ? 0 : stage + 1;
       const uint32_t nphase = (nstage == 0) ? (phase ^ 1u) : phase;
       const bool more = c + 1 < nchunks;
@@ -421,7 +476,8 @@ __global__ void __launch_bounds__(NTHREADS, 1)
       const int base = c * BK + 2 * t;  // this thread's first reduction point of the chunk, counted from `begin`
 #pragma unroll
       for (int blk = 0; blk < NBLK; ++blk) {
-        double kn[LA][2][RT];  // the next block: of this chunk, or the first of the tile's next chunk
+        double (&kc)[LA][2][RT] = (blk & 1) ? k1 : k0;
+        double (&kn)[LA][2][RT] = (blk & 1) ? k0 : k1;  // the next block: of this chunk, or the first of the tile's next chunk
         if (blk + 1 < NBLK) {
           gram_block(Pt, (blk + 1) * LA, base + 8 * (blk + 1) * LA, kn);
         } else if (more) {
@@ -433,15 +489,6 @@ __global__ void __launch_bounds__(NTHREADS, 1)
           const unsigned char* bgrp = bchunk + (blk * LA + q) * 1024;
           mma_step(bgrp + off0, kc[q][0]);
           mma_step(bgrp + off1, kc[q][1]);
-        }
-        if (blk + 1 < NBLK || more) {
-#pragma unroll
-          for (int q = 0; q < LA; ++q)
-#pragma unroll
-            for (int h = 0; h < RT; ++h) {
-              kc[q][0][h] = kn[q][0][h];
-              kc[q][1][h] = kn[q][1][h];
-            }
         }
       }
       // chunk gc fully consumed by this warp.  The last warp to release a stage refills it with chunk gc + STAGES (which may
@@ -456,6 +503,17 @@ __global__ void __launch_bounds__(NTHREADS, 1)
       }
       stage = nstage;
       phase = nphase;
+      ++gc;
+    };
+#pragma unroll 1
+    for (int c = 0; c < nchunks;) {
+      run_chunk(c, kA, kB);
+      ++c;
+      if (NBLK & 1) {  // the successor block sits in kB: run the next chunk with the sets swapped
+        if (c >= nchunks) break;
+        run_chunk(c, kB, kA);
+        ++c;
+      }
     }
     const int estage = (stage == 0) ? STAGES - 1 : stage - 1;  // the stage of the tile's last chunk
 
@@ -678,9 +736,10 @@ __global__ void __launch_bounds__(NTHREADS, 1)
   }
 }
 
-template <int NKD, bool BACKWARD, bool RBF, int RT, int EPI>
+template <int NKD, bool BACKWARD, int KSRC, int RT, int EPI>
 cudaError_t launch_one(const pls_ctx* ctx, GenGemmParams p, cudaStream_t stream) {
   using T = Tile<RT>;
+  if (KSRC == KSRC_CACHED) p.sp = 0;  // no point rows are staged
   int64_t grid = ((p.n_rows + T::BR - 1) / T::BR) * ((p.j + T::BJ - 1) / T::BJ);
   if (BACKWARD) grid *= p.splits;
   else {
@@ -702,9 +761,9 @@ cudaError_t launch_one(const pls_ctx* ctx, GenGemmParams p, cudaStream_t stream)
   cudaError_t e = make_stream_maps(ctx, p.b, p.red_total, p.ldb, T::NPR, &tm3, &tm2, &p.tma3d);
   if (e != cudaSuccess) return e;
   p.full_blocks = p.ldb / 16;
-  e = cudaFuncSetAttribute(gen_gemm_kernel<NKD, BACKWARD, RBF, RT, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  e = cudaFuncSetAttribute(gen_gemm_kernel<NKD, BACKWARD, KSRC, RT, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  gen_gemm_kernel<NKD, BACKWARD, RBF, RT, EPI><<<(unsigned)grid, NTHREADS, smem, stream>>>(p, tm3, tm2);
+  gen_gemm_kernel<NKD, BACKWARD, KSRC, RT, EPI><<<(unsigned)grid, NTHREADS, smem, stream>>>(p, tm3, tm2);
   return cudaGetLastError();
 }
 
@@ -712,9 +771,16 @@ cudaError_t launch_one(const pls_ctx* ctx, GenGemmParams p, cudaStream_t stream)
 template <int NKD, int ROLE>
 cudaError_t launch_role(const pls_ctx* ctx, const GenGemmParams& p, cudaStream_t stream) {
   constexpr bool BW = ROLE < 0;
+  if (p.gram) {  // the cached-Gram kernels do not depend on the exponent depth: they live in the NKD = 1 units only
+    if constexpr (NKD == 1) {
+      return (p.rt == 1) ? launch_one<1, BW, KSRC_CACHED, 1, ROLE>(ctx, p, stream) : launch_one<1, BW, KSRC_CACHED, 2, ROLE>(ctx, p, stream);
+    } else {
+      return cudaErrorInvalidValue;
+    }
+  }
   const bool rbf = (p.kernel_id == PLS_KERNEL_RBF);
-  if (p.rt == 1) return rbf ? launch_one<NKD, BW, true, 1, ROLE>(ctx, p, stream) : launch_one<NKD, BW, false, 1, ROLE>(ctx, p, stream);
-  return rbf ? launch_one<NKD, BW, true, 2, ROLE>(ctx, p, stream) : launch_one<NKD, BW, false, 2, ROLE>(ctx, p, stream);
+  if (p.rt == 1) return rbf ? launch_one<NKD, BW, KSRC_RBF, 1, ROLE>(ctx, p, stream) : launch_one<NKD, BW, KSRC_LINEAR, 1, ROLE>(ctx, p, stream);
+  return rbf ? launch_one<NKD, BW, KSRC_RBF, 2, ROLE>(ctx, p, stream) : launch_one<NKD, BW, KSRC_LINEAR, 2, ROLE>(ctx, p, stream);
 }
 
 }  // namespace

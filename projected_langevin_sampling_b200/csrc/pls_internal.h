@@ -26,6 +26,8 @@ struct GenGemmParams {
   int64_t n_rows;
   const double* red_aug;  // reduction-side augmented points (red_total x sp)
   int64_t red_total;
+  const double* gram;  // optional cached Gram (training rows x inducing columns, ldk): replaces the generated values
+  int64_t ldk;
   const double* b;  // streamed matrix (red_total x ldb)
   int64_t ldb;
   int64_t j;  // valid columns

@@ -5,18 +5,21 @@ One step (reference: PLS.calculate_particle_update, src/projected_langevin_sampl
 
     W  = V~ P                                  pls_gemm_f64            (M x J; 2 M M_k J flops)
     for each chunk of training rows:
-        Dc = d_2 c(y, k(X_c, Z) W)             pls_forward_f64         (Gram tiles generated on the fly, cost in registers)
-        Gp += k(Z, X_c) Dc                     pls_backward_f64        (Gram tiles generated on the fly, split over rows)
+        Dc = d_2 c(y, k(X_c, Z) W)             pls_forward[_cached]_f64   (Gram tiles generated on the fly or loaded, cost in registers)
+        Gp += k(Z, X_c) Dc                     pls_backward[_cached]_f64  (likewise, split over rows)
     G' = sum_s Gp[s]                           pls_reduce_splits_f64   (deterministic order)
     [all-reduce G' over the N-shard group]     torch.distributed / NCCL, only when the training rows are sharded
     P += -eta V~^T G' - eta P / lambda + sqrt(2 eta) xi      pls_project_update_f64
 
-The N x M Gram and the N x J prediction matrix are never materialised; the only N-sized intermediate is the Dc chunk
-(`dc_budget_bytes`, default 8 GiB), written and read once per step (~2 % of the step time at the headline shape).
+The N x J prediction matrix is never materialised; the only N x J intermediate is the Dc chunk (`dc_budget_bytes`, default
+8 GiB), written and read once per step (~2 % of the step time at the headline shape).  The N x M Gram is generated inside the
+kernels from the points, or -- `gram_cache`, when N x M doubles fit comfortably (the reference keeps k(Z, X) for the whole run,
+orthonormal.py:36-41) -- computed once and streamed, which takes the exponent work off the FP64 pipe.
 """
 from __future__ import annotations
 
-from typing import Callable, List, Optional, Tuple
+import os
+from typing import Callable, List, Optional, Tuple, Union
 
 import torch
 
@@ -25,14 +28,30 @@ from . import ops
 
 DEFAULT_DC_BUDGET = 8 << 30
 ROW_ALIGN = 128
+DEFAULT_GRAM_CACHE_BYTES = 24 << 30
+
+
+def want_gram_cache(mode: Union[bool, str, None], ctx: nat.Context, n: int, m: int, device: torch.device) -> bool:
+    """Policy for keeping k(X, Z) resident.  mode: True / "on", False / "off", or "auto" (default; the environment variable
+    PLS_B200_GRAM_CACHE overrides it): cache when it takes at most PLS_B200_GRAM_CACHE_BYTES (24 GiB) and a third of the free
+    device memory."""
+    mode = os.environ.get("PLS_B200_GRAM_CACHE", mode if mode is not None else "auto")
+    if mode in (True, "on", "1", "true"):
+        return True
+    if mode in (False, "off", "0", "false"):
+        return False
+    nbytes = int(ctx.lib.pls_gram_cache_rows(n)) * int(ctx.lib.pls_gram_cache_ld(m)) * 8
+    free, _ = torch.cuda.mem_get_info(device)
+    return n > 0 and m > 0 and nbytes <= int(os.environ.get("PLS_B200_GRAM_CACHE_BYTES", DEFAULT_GRAM_CACHE_BYTES)) and nbytes <= free // 3
 
 
 class LangevinEngine:
     def __init__(self, ctx: nat.Context, kernel_id: int, d: int, xa: torch.Tensor, za: torch.Tensor, vt: torch.Tensor,
                  inv_lambda: torch.Tensor, j: int, dc_budget_bytes: int = DEFAULT_DC_BUDGET,
                  gradient_reduce: Optional[Callable[[torch.Tensor], None]] = None,
-                 weights_fn: Optional[Callable[[torch.Tensor, torch.Tensor], None]] = None):
+                 weights_fn: Optional[Callable[[torch.Tensor, torch.Tensor], None]] = None, gram: Optional[torch.Tensor] = None):
         self.ctx, self.kernel_id, self.d = ctx, kernel_id, d
+        self.gram = gram  # ops.gram_cache(...) of (xa, za) or None: Gram values loaded instead of generated
         self.xa, self.za, self.vt, self.inv_lambda = xa, za, vt, inv_lambda
         self.n, self.m, self.m_k, self.j = xa.shape[0], za.shape[0], vt.shape[1], j
         self.gradient_reduce = gradient_reduce
@@ -52,6 +71,9 @@ class LangevinEngine:
         self._zeros: Optional[torch.Tensor] = None
 
     # ---- pieces ------------------------------------------------------------------------------------------------------
+    def _gram(self, r0: int = 0) -> Optional[torch.Tensor]:
+        return None if self.gram is None else self.gram[r0:]
+
     def _weights(self, particles: torch.Tensor) -> torch.Tensor:
         if self.weights_fn is not None:
             self.weights_fn(particles, self.w)  # e.g. W = k(Z, Z)^{-1} P for the InducingPointBasis
@@ -72,13 +94,13 @@ class LangevinEngine:
             if with_cost:
                 t1 = t0 + (r1 - r0 + self.tile_rows - 1) // self.tile_rows
                 ops.forward_step(self.ctx, self.kernel_id, self.xa[r0:r1], self.za, self.d, self.w, self.j, cost, y[r0:r1], dc,
-                                 self.cost_partial[t0:t1])
+                                 self.cost_partial[t0:t1], gram=self._gram(r0))
                 t0 = t1
             else:
                 ops.forward(self.ctx, self.kernel_id, self.xa[r0:r1], self.za, self.d, self.w, self.j, nat.EPI_COST_DERIVATIVE,
-                            dc, cost=cost, y=y[r0:r1])
+                            dc, cost=cost, y=y[r0:r1], gram=self._gram(r0))
             ops.backward(self.ctx, self.kernel_id, self.za, self.xa[r0:r1], self.d, dc, self.j, self.gp, self.splits,
-                         accumulate=ci > 0)
+                         accumulate=ci > 0, gram=self._gram(r0))
         ops.reduce_splits(self.ctx, self.gp, self.j, self.gm)
         if self.gradient_reduce is not None:
             self.gradient_reduce(self.gm)
@@ -118,13 +140,14 @@ class LangevinEngine:
         """F = k(X, Z) V~ P  -> (N, J)  (materialised: API parity / small problems only)."""
         self._weights(particles)
         out, _ = ops.alloc_matrix(self.n, self.j, self.xa.device)
-        ops.forward(self.ctx, self.kernel_id, self.xa, self.za, self.d, self.w, self.j, nat.EPI_PREDICTION, out)
+        ops.forward(self.ctx, self.kernel_id, self.xa, self.za, self.d, self.w, self.j, nat.EPI_PREDICTION, out, gram=self._gram())
         return out[:, : self.j]
 
     def cost_derivative(self, particles: torch.Tensor, cost: nat.PlsCost, y: torch.Tensor) -> torch.Tensor:
         self._weights(particles)
         out, _ = ops.alloc_matrix(self.n, self.j, self.xa.device)
-        ops.forward(self.ctx, self.kernel_id, self.xa, self.za, self.d, self.w, self.j, nat.EPI_COST_DERIVATIVE, out, cost=cost, y=y)
+        ops.forward(self.ctx, self.kernel_id, self.xa, self.za, self.d, self.w, self.j, nat.EPI_COST_DERIVATIVE, out, cost=cost, y=y,
+                    gram=self._gram())
         return out[:, : self.j]
 
     def cost_partials(self, particles: torch.Tensor, cost: nat.PlsCost, y: torch.Tensor) -> torch.Tensor:
@@ -133,7 +156,7 @@ class LangevinEngine:
         tile_rows = ops.forward_tile_rows(self.ctx, self.j)
         tiles = (self.n + tile_rows - 1) // tile_rows
         part = torch.empty((max(tiles, 1), self.ldj), dtype=torch.float64, device=self.xa.device)
-        ops.forward(self.ctx, self.kernel_id, self.xa, self.za, self.d, self.w, self.j, nat.EPI_COST, part, cost=cost, y=y)
+        ops.forward(self.ctx, self.kernel_id, self.xa, self.za, self.d, self.w, self.j, nat.EPI_COST, part, cost=cost, y=y, gram=self._gram())
         return part
 
     def cost(self, particles: torch.Tensor, cost: nat.PlsCost, y: torch.Tensor) -> torch.Tensor:
@@ -152,7 +175,7 @@ class LangevinEngine:
             dc = buf[:, : self.j]
         splits = ops.backward_splits(self.ctx, self.n, self.m, self.j)
         gp = torch.empty((splits, self.m, self.ldj), dtype=torch.float64, device=dc.device)
-        ops.backward(self.ctx, self.kernel_id, self.za, self.xa, self.d, dc, self.j, gp, splits, accumulate=False)
+        ops.backward(self.ctx, self.kernel_id, self.za, self.xa, self.d, dc, self.j, gp, splits, accumulate=False, gram=self._gram())
         ops.reduce_splits(self.ctx, gp, self.j, self.gm)
         if self.gradient_reduce is not None:
             self.gradient_reduce(self.gm)

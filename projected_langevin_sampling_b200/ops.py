@@ -79,31 +79,60 @@ def gemm(ctx: nat.Context, a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, 
     return out
 
 
+def gram_cache(ctx: nat.Context, kernel_id: int, rows_aug: torch.Tensor, cols_aug: torch.Tensor, d: int, chunk: int = 262144) -> torch.Tensor:
+    """k(X, Z) kept resident for the pls_*_cached_f64 entry points: (pls_gram_cache_rows(N), pls_gram_cache_ld(M)) float64,
+    zero padding, filled by pls_gram_f64 in row chunks.  Pass `cache[r0:]` as `gram=` for the rows starting at r0."""
+    n, m = rows_aug.shape[0], cols_aug.shape[0]
+    k = torch.zeros((int(ctx.lib.pls_gram_cache_rows(n)), int(ctx.lib.pls_gram_cache_ld(m))), dtype=F64, device=rows_aug.device)
+    for r0 in range(0, n, chunk):
+        r1 = min(n, r0 + chunk)
+        ctx.check(ctx.lib.pls_gram_f64(ctx.handle, kernel_id, rows_aug[r0:r1].data_ptr(), r1 - r0, cols_aug.data_ptr(), m, d,
+                                       k[r0:].data_ptr(), k.shape[1], ctx.stream()))
+        ctx.launches += 1
+    return k
+
+
 def forward(ctx: nat.Context, kernel_id: int, xa: torch.Tensor, za: torch.Tensor, d: int, w: torch.Tensor, j: int,
-            epilogue: int, out: torch.Tensor, cost: Optional[nat.PlsCost] = None, y: Optional[torch.Tensor] = None) -> torch.Tensor:
-    ctx.check(ctx.lib.pls_forward_f64(ctx.handle, kernel_id, xa.data_ptr(), xa.shape[0], za.data_ptr(), za.shape[0], d,
-                                      w.data_ptr(), _ld(w), j, epilogue, C.byref(cost) if cost is not None else None,
-                                      nat.ptr(y), out.data_ptr(), _ld(out), ctx.stream()))
+            epilogue: int, out: torch.Tensor, cost: Optional[nat.PlsCost] = None, y: Optional[torch.Tensor] = None,
+            gram: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """gram: rows [r0, ...) of a gram_cache() for the rows of xa -- the Gram values are then loaded, not generated."""
+    costp = C.byref(cost) if cost is not None else None
+    if gram is not None:
+        ctx.check(ctx.lib.pls_forward_cached_f64(ctx.handle, gram.data_ptr(), _ld(gram), xa.shape[0], za.shape[0], w.data_ptr(), _ld(w),
+                                                 j, epilogue, costp, nat.ptr(y), out.data_ptr(), _ld(out), ctx.stream()))
+    else:
+        ctx.check(ctx.lib.pls_forward_f64(ctx.handle, kernel_id, xa.data_ptr(), xa.shape[0], za.data_ptr(), za.shape[0], d,
+                                          w.data_ptr(), _ld(w), j, epilogue, costp, nat.ptr(y), out.data_ptr(), _ld(out), ctx.stream()))
     ctx.launches += 1
     return out
 
 
 def forward_step(ctx: nat.Context, kernel_id: int, xa: torch.Tensor, za: torch.Tensor, d: int, w: torch.Tensor, j: int,
-                 cost: nat.PlsCost, y: torch.Tensor, dc: torch.Tensor, cost_partial: torch.Tensor) -> None:
+                 cost: nat.PlsCost, y: torch.Tensor, dc: torch.Tensor, cost_partial: torch.Tensor,
+                 gram: Optional[torch.Tensor] = None) -> None:
     """Forward with the cost derivative AND the per-row-tile cost sums from the same F tile (pls_forward_step_f64)."""
-    ctx.check(ctx.lib.pls_forward_step_f64(ctx.handle, kernel_id, xa.data_ptr(), xa.shape[0], za.data_ptr(), za.shape[0], d,
-                                           w.data_ptr(), _ld(w), j, C.byref(cost), y.data_ptr(), dc.data_ptr(), _ld(dc),
-                                           cost_partial.data_ptr(), _ld(cost_partial), ctx.stream()))
+    if gram is not None:
+        ctx.check(ctx.lib.pls_forward_step_cached_f64(ctx.handle, gram.data_ptr(), _ld(gram), xa.shape[0], za.shape[0], w.data_ptr(),
+                                                      _ld(w), j, C.byref(cost), y.data_ptr(), dc.data_ptr(), _ld(dc),
+                                                      cost_partial.data_ptr(), _ld(cost_partial), ctx.stream()))
+    else:
+        ctx.check(ctx.lib.pls_forward_step_f64(ctx.handle, kernel_id, xa.data_ptr(), xa.shape[0], za.data_ptr(), za.shape[0], d,
+                                               w.data_ptr(), _ld(w), j, C.byref(cost), y.data_ptr(), dc.data_ptr(), _ld(dc),
+                                               cost_partial.data_ptr(), _ld(cost_partial), ctx.stream()))
     ctx.launches += 1
 
 
 def backward(ctx: nat.Context, kernel_id: int, za: torch.Tensor, xa: torch.Tensor, d: int, dc: torch.Tensor, j: int,
-             gp: torch.Tensor, splits: int, accumulate: bool) -> torch.Tensor:
-    """gp: (splits, M, ld) storage."""
+             gp: torch.Tensor, splits: int, accumulate: bool, gram: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """gp: (splits, M, ld) storage.  gram: as in forward()."""
     assert gp.dim() == 3 and gp.shape[0] == splits and gp.shape[1] == za.shape[0] and gp.is_contiguous()
-    ctx.check(ctx.lib.pls_backward_f64(ctx.handle, kernel_id, za.data_ptr(), za.shape[0], xa.data_ptr(), xa.shape[0], d,
-                                       dc.data_ptr(), _ld(dc), j, gp.data_ptr(), gp.shape[2], splits, int(accumulate),
-                                       ctx.stream()))
+    if gram is not None:
+        ctx.check(ctx.lib.pls_backward_cached_f64(ctx.handle, gram.data_ptr(), _ld(gram), za.shape[0], xa.shape[0], dc.data_ptr(),
+                                                  _ld(dc), j, gp.data_ptr(), gp.shape[2], splits, int(accumulate), ctx.stream()))
+    else:
+        ctx.check(ctx.lib.pls_backward_f64(ctx.handle, kernel_id, za.data_ptr(), za.shape[0], xa.data_ptr(), xa.shape[0], d,
+                                           dc.data_ptr(), _ld(dc), j, gp.data_ptr(), gp.shape[2], splits, int(accumulate),
+                                           ctx.stream()))
     ctx.launches += 1
     return gp
 

@@ -13,7 +13,7 @@ import torch
 
 from ... import _native as nat
 from ... import ops
-from ...engine import DEFAULT_DC_BUDGET, LangevinEngine
+from ...engine import DEFAULT_DC_BUDGET, LangevinEngine, want_gram_cache
 from ...kernels import dense_gram, kernel_spec
 from ...samplers import langevin_noise, sample_multivariate_normal
 from .base import PLSBasis
@@ -31,14 +31,19 @@ class OrthonormalBasis(PLSBasis):
       dc_budget_bytes     size cap of the d_2 c row-chunk workspace of the fused step
       gradient_reduce     callable applied in place to the (M, J) gradient before the update (NCCL all-reduce when
                           the training rows are sharded across GPUs)
+      gram_cache          "auto" (default) / True / False: keep k(X, Z) resident in HBM, as the reference does
+                          (orthonormal.py:36-41), and stream it instead of regenerating it in the kernels; "auto" does so
+                          when it fits comfortably (engine.want_gram_cache)
     """
 
     def __init__(self, kernel, x_induce: torch.Tensor, x_train: torch.Tensor, eigenvalue_threshold: float = 0.0,
                  additional_predictive_noise_distribution: Optional[torch.distributions.Distribution] = None, *,
                  eigendecomposition: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, eigh_device: str = "cpu",
-                 dc_budget_bytes: int = DEFAULT_DC_BUDGET, gradient_reduce=None, verbose: bool = True):
+                 dc_budget_bytes: int = DEFAULT_DC_BUDGET, gradient_reduce=None, verbose: bool = True,
+                 gram_cache="auto"):
         super().__init__(additional_predictive_noise_distribution=additional_predictive_noise_distribution)
         self.kernel = kernel
+        self._gram_cache_mode, self._gram = gram_cache, None
         self.ctx = nat.context()
         dev = torch.device("cuda", self.ctx.device_index)
         self.x_induce = ops.as_device_f64(x_induce if x_induce.dim() > 1 else x_induce.unsqueeze(-1), dev)  # (M, D)
@@ -95,9 +100,11 @@ class OrthonormalBasis(PLSBasis):
         eng = self._engines.get(number_of_particles)
         if eng is None:
             self._engines.clear()  # one set of workspaces at a time
+            if self._gram is None and want_gram_cache(self._gram_cache_mode, self.ctx, self._xa.shape[0], self._za.shape[0], self._xa.device):
+                self._gram = ops.gram_cache(self.ctx, self._spec.kernel_id, self._xa, self._za, self._d)  # k(X, Z), once
             eng = LangevinEngine(self.ctx, self._spec.kernel_id, self._d, self._xa, self._za, self.scaled_eigenvectors,
                                  self._inv_lambda, number_of_particles, dc_budget_bytes=self._dc_budget,
-                                 gradient_reduce=self._gradient_reduce)
+                                 gradient_reduce=self._gradient_reduce, gram=self._gram)
             self._engines[number_of_particles] = eng
         return eng
 

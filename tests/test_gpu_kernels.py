@@ -269,8 +269,8 @@ def _random_shapes(count, seed):
 @pytest.mark.parametrize("n,m,d,j,ld", _random_shapes(14, seed=2024))
 def test_generated_operand_gemm_random_shapes(ctx, n, m, d, j, ld):
     """Seeded random (N, M, D, J, leading dimension) draws -- ragged tiles, every exponent depth, one- and many-stage
-    reductions, persistent CTAs with zero, one or several tiles: all four forward epilogues and the backward role against
-    dense float64 torch algebra on pls_gram_f64's matrix."""
+    reductions, persistent CTAs with zero, one or several tiles: all four forward epilogues and the backward role, with
+    generated and with cached Gram values, against dense float64 torch algebra on pls_gram_f64's matrix."""
     from projected_langevin_sampling_b200 import _native as nat, ops
 
     g = torch.Generator().manual_seed(n * 7919 + m * 31 + j)
@@ -291,26 +291,33 @@ def test_generated_operand_gemm_random_shapes(ctx, n, m, d, j, ld):
     e = want_f - y[:, None]
     want_dc = 5.0 * e / (4.0 * 0.49 + e * e)
     want_c = (2.5 * torch.log(1.0 + e * e / (4.0 * 0.49))).sum(0)
-    f = torch.full((n, ld), 3.0, dtype=torch.float64).cuda()
-    ops.forward(ctx, nat.KERNEL_RBF, xa, za, d, w, j, nat.EPI_PREDICTION, f)
-    assert (f[:, :j] - want_f).abs().max().item() < 1e-12 * scale and (f[:, j:] == 3.0).all()
-    dc = torch.full((n, ld), 3.0, dtype=torch.float64).cuda()
-    ops.forward(ctx, nat.KERNEL_RBF, xa, za, d, w, j, nat.EPI_COST_DERIVATIVE, dc, cost=cost, y=y)
-    assert (dc[:, :j] - want_dc).abs().max().item() < 1e-11 * max(1.0, want_dc.abs().max().item()) and (dc[:, j:] == 3.0).all()
-    tiles = (n + ops.forward_tile_rows(ctx, j) - 1) // ops.forward_tile_rows(ctx, j)
-    part = torch.zeros(tiles, ld, dtype=torch.float64).cuda()
-    ops.forward(ctx, nat.KERNEL_RBF, xa, za, d, w, j, nat.EPI_COST, part, cost=cost, y=y)
-    assert (part[:, :j].sum(0) - want_c).abs().max().item() < 1e-11 * max(1.0, want_c.abs().max().item())
-    dc2 = torch.full((n, ld), 4.0, dtype=torch.float64).cuda()
-    part2 = torch.zeros(tiles, ld, dtype=torch.float64).cuda()
-    ops.forward_step(ctx, nat.KERNEL_RBF, xa, za, d, w, j, cost, y, dc2, part2)
-    assert (dc2[:, :j] - want_dc).abs().max().item() < 1e-11 * max(1.0, want_dc.abs().max().item()) and (dc2[:, j:] == 4.0).all()
-    assert (part2[:, :j].sum(0) - want_c).abs().max().item() < 1e-11 * max(1.0, want_c.abs().max().item())
-    dcin = torch.randn(n, ld, generator=g, dtype=torch.float64).cuda()
-    want_g = k_xz.T @ dcin[:, :j]
-    splits = ops.backward_splits(ctx, n, m, j)
-    gp = torch.full((splits, m, ld), -2.0, dtype=torch.float64).cuda()
-    ops.backward(ctx, nat.KERNEL_RBF, za, xa, d, dcin, j, gp, splits, accumulate=False)
-    out = torch.empty(m, ld, dtype=torch.float64).cuda()
-    ops.reduce_splits(ctx, gp, j, out)
-    assert (out[:, :j] - want_g).abs().max().item() < 1e-11 * max(1.0, want_g.abs().max().item()) and (gp[:, :, j:] == -2.0).all()
+    # generated Gram values, then the same launches with the Gram cached in HBM (pls_*_cached_f64) -- offset into a larger cache
+    # so that the row padding the kernels may read holds OTHER rows' (finite, non-zero) values, as in the engine's row chunks
+    wrap = torch.arange(256, device=xa.device) % n
+    big = ops.gram_cache(ctx, nat.KERNEL_RBF, torch.cat([xa[wrap], xa, xa[wrap]]), za, d)
+    assert big.shape[1] == (m + 127) // 128 * 128 and big.shape[0] % 128 == 0 and torch.equal(big[256:256 + n, :m], k_xz)
+    big[:, m:] = 0.37  # column padding: read, multiplied by zero rows of the streamed matrix, must only be finite
+    for gram in (None, big[256:]):
+        f = torch.full((n, ld), 3.0, dtype=torch.float64).cuda()
+        ops.forward(ctx, nat.KERNEL_RBF, xa, za, d, w, j, nat.EPI_PREDICTION, f, gram=gram)
+        assert (f[:, :j] - want_f).abs().max().item() < 1e-12 * scale and (f[:, j:] == 3.0).all()
+        dc = torch.full((n, ld), 3.0, dtype=torch.float64).cuda()
+        ops.forward(ctx, nat.KERNEL_RBF, xa, za, d, w, j, nat.EPI_COST_DERIVATIVE, dc, cost=cost, y=y, gram=gram)
+        assert (dc[:, :j] - want_dc).abs().max().item() < 1e-11 * max(1.0, want_dc.abs().max().item()) and (dc[:, j:] == 3.0).all()
+        tiles = (n + ops.forward_tile_rows(ctx, j) - 1) // ops.forward_tile_rows(ctx, j)
+        part = torch.zeros(tiles, ld, dtype=torch.float64).cuda()
+        ops.forward(ctx, nat.KERNEL_RBF, xa, za, d, w, j, nat.EPI_COST, part, cost=cost, y=y, gram=gram)
+        assert (part[:, :j].sum(0) - want_c).abs().max().item() < 1e-11 * max(1.0, want_c.abs().max().item())
+        dc2 = torch.full((n, ld), 4.0, dtype=torch.float64).cuda()
+        part2 = torch.zeros(tiles, ld, dtype=torch.float64).cuda()
+        ops.forward_step(ctx, nat.KERNEL_RBF, xa, za, d, w, j, cost, y, dc2, part2, gram=gram)
+        assert (dc2[:, :j] - want_dc).abs().max().item() < 1e-11 * max(1.0, want_dc.abs().max().item()) and (dc2[:, j:] == 4.0).all()
+        assert (part2[:, :j].sum(0) - want_c).abs().max().item() < 1e-11 * max(1.0, want_c.abs().max().item())
+        dcin = torch.randn(n, ld, generator=g, dtype=torch.float64).cuda()
+        want_g = k_xz.T @ dcin[:, :j]
+        splits = ops.backward_splits(ctx, n, m, j)
+        gp = torch.full((splits, m, ld), -2.0, dtype=torch.float64).cuda()
+        ops.backward(ctx, nat.KERNEL_RBF, za, xa, d, dcin, j, gp, splits, accumulate=False, gram=gram)
+        out = torch.empty(m, ld, dtype=torch.float64).cuda()
+        ops.reduce_splits(ctx, gp, j, out)
+        assert (out[:, :j] - want_g).abs().max().item() < 1e-11 * max(1.0, want_g.abs().max().item()) and (gp[:, :, j:] == -2.0).all()

@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--kernel", type=str, default="rbf", choices=["rbf", "linear"])
     ap.add_argument("--cost", type=str, default="gaussian", choices=["gaussian", "poisson", "bernoulli", "student_t", "multimodal"])
     ap.add_argument("--roles", type=str, default="forward,backward")
+    ap.add_argument("--cached", action="store_true", help="stream a resident Gram (pls_*_cached_f64) instead of generating it")
     args = ap.parse_args()
 
     kid = nat.KERNEL_RBF if args.kernel == "rbf" else nat.KERNEL_LINEAR
@@ -64,7 +65,8 @@ def main():
     splits = args.splits or ops.backward_splits(ctx, n, m, j)
     gp = torch.zeros(splits, m, j, dtype=torch.float64).cuda()
     flops = 2.0 * n * m * j
-    res = {"n": n, "m": m, "d": d, "j": j, "rt": args.rt, "epilogue": args.epilogue, "kernel": args.kernel, "cost": args.cost, "splits": splits}
+    gram = ops.gram_cache(ctx, kid, xa, za, d) if args.cached else None
+    res = {"cached": bool(args.cached), "n": n, "m": m, "d": d, "j": j, "rt": args.rt, "epilogue": args.epilogue, "kernel": args.kernel, "cost": args.cost, "splits": splits}
 
     def timed(fn):
         fn()
@@ -82,12 +84,12 @@ def main():
     if "forward" in args.roles:
         if args.epilogue == nat.EPI_COST_DERIVATIVE_AND_COST:
             part = torch.zeros((n + tile_rows - 1) // tile_rows, j, dtype=torch.float64).cuda()
-            ms = timed(lambda: ops.forward_step(ctx, kid, xa, za, d, w, j, cost, y, out, part))
+            ms = timed(lambda: ops.forward_step(ctx, kid, xa, za, d, w, j, cost, y, out, part, gram=gram))
         else:
-            ms = timed(lambda: ops.forward(ctx, kid, xa, za, d, w, j, args.epilogue, out, cost=cost, y=y))
+            ms = timed(lambda: ops.forward(ctx, kid, xa, za, d, w, j, args.epilogue, out, cost=cost, y=y, gram=gram))
         res["forward_ms"], res["forward_tflops"] = round(ms, 3), round(flops / ms / 1e9, 3)
     if "backward" in args.roles:
-        ms = timed(lambda: ops.backward(ctx, kid, za, xa, d, dc, j, gp, splits, accumulate=False))
+        ms = timed(lambda: ops.backward(ctx, kid, za, xa, d, dc, j, gp, splits, accumulate=False, gram=gram))
         res["backward_ms"], res["backward_tflops"] = round(ms, 3), round(flops / ms / 1e9, 3)
     print(json.dumps(res))
 
