@@ -69,13 +69,13 @@ def synth(workload: dict, seed: int = 0):
     return x, y, x[z_idx].clone(), ls, outputscale
 
 
-def make_pls(workload: dict, x, y, z, ls, outputscale, gradient_reduce=None):
+def make_pls(workload: dict, x, y, z, ls, outputscale, gradient_reduce=None, gram_cache="auto"):
     import projected_langevin_sampling_b200 as pkg
     from projected_langevin_sampling_b200.projected_langevin_sampling import costs, link_functions as lf
 
     kernel = pkg.ScaleKernel(pkg.RBFKernel(ard_num_dims=x.shape[1], lengthscale=ls), outputscale=outputscale)
     basis = pkg.OrthonormalBasis(pkg.PLSKernel(kernel, z), z, x, eigenvalue_threshold=workload.get("threshold", 0.0), verbose=False,
-                                 gradient_reduce=gradient_reduce)
+                                 gradient_reduce=gradient_reduce, gram_cache=gram_cache)
     if workload["cost"] == "gaussian":
         cost = costs.GaussianCost(observation_noise=0.01, y_train=y, link_function=lf.IdentityLinkFunction())
     elif workload["cost"] == "bernoulli":
@@ -292,22 +292,22 @@ class KernelTimer:
         timer = self
         orig_fwd, orig_bwd = ops.forward, ops.backward
 
-        def fwd(ctx, kernel_id, xa, za, d, w, j, epilogue, out, cost=None, y=None):
+        def fwd(ctx, kernel_id, xa, za, d, w, j, epilogue, out, **kw):
             if not timer.enabled:
-                return orig_fwd(ctx, kernel_id, xa, za, d, w, j, epilogue, out, cost=cost, y=y)
+                return orig_fwd(ctx, kernel_id, xa, za, d, w, j, epilogue, out, **kw)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            r = orig_fwd(ctx, kernel_id, xa, za, d, w, j, epilogue, out, cost=cost, y=y)
+            r = orig_fwd(ctx, kernel_id, xa, za, d, w, j, epilogue, out, **kw)
             e1.record()
             timer.records.append(("forward", 2.0 * xa.shape[0] * za.shape[0] * j, e0, e1))
             return r
 
-        def bwd(ctx, kernel_id, za, xa, d, dc, j, gp, splits, accumulate):
+        def bwd(ctx, kernel_id, za, xa, d, dc, j, gp, splits, accumulate, **kw):
             if not timer.enabled:
-                return orig_bwd(ctx, kernel_id, za, xa, d, dc, j, gp, splits, accumulate)
+                return orig_bwd(ctx, kernel_id, za, xa, d, dc, j, gp, splits, accumulate, **kw)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            r = orig_bwd(ctx, kernel_id, za, xa, d, dc, j, gp, splits, accumulate)
+            r = orig_bwd(ctx, kernel_id, za, xa, d, dc, j, gp, splits, accumulate, **kw)
             e1.record()
             timer.records.append(("backward", 2.0 * xa.shape[0] * za.shape[0] * j, e0, e1))
             return r
@@ -362,6 +362,9 @@ def main():
     ap.add_argument("--grid", type=str, default=None,
                     help="RxC = row shards x particle shards of ONE problem (strong scaling; needs R*C == world). Default: every GPU "
                          "advances its own J particles against replicated data (weak scaling in J, no communication)")
+    ap.add_argument("--gram", type=str, default="auto", choices=["auto", "cached", "generated"],
+                    help="k(X, Z) kept resident in HBM and streamed (cached) or regenerated inside the kernels (generated); auto caches "
+                         "when it fits comfortably (engine.want_gram_cache) -- C4: 8.6 GB per GPU")
     ap.add_argument("--rows", dest="n", type=int, default=None, help="override N (debugging; the line then names the reduced workload)")
     ap.add_argument("--particles", dest="j", type=int, default=None)
     args = ap.parse_args()
@@ -394,6 +397,7 @@ def main():
     ctx = _native.context()
     t_setup = time.perf_counter()
     x, y, z, ls, outputscale = synth(workload)
+    gram_mode = {"auto": "auto", "cached": True, "generated": False}[args.gram]
     grid = None
     if args.grid:
         from projected_langevin_sampling_b200.distributed import GridPlacement, gradient_allreduce, make_row_group
@@ -403,17 +407,21 @@ def main():
         row_group = make_row_group(grid) if world > 1 else None
         r0, r1 = grid.rows(workload["n"])
         j_off, j_end = grid.particles(workload["j"])
-        pls = make_pls(workload, x[r0:r1].contiguous(), y[r0:r1].contiguous(), z, ls, outputscale, gradient_allreduce(row_group))
+        pls = make_pls(workload, x[r0:r1].contiguous(), y[r0:r1].contiguous(), z, ls, outputscale, gradient_allreduce(row_group),
+                       gram_cache=gram_mode)
         j_local = j_end - j_off
         del x, y
     else:
-        pls = make_pls(workload, x, y, z, ls, outputscale)
+        pls = make_pls(workload, x, y, z, ls, outputscale, gram_cache=gram_mode)
         j_local = workload["j"]  # weak scaling: every GPU owns J particles
         j_off = rank * j_local
     m_k = pls.basis.approximation_dimension
     lam_min = float(pls.basis.eigenvalues.min())
     eta = 1e-9 if workload["cost"] == "gaussian" else 1e-6
     particles = pls.initialise_particles(j_local, seed=1000 + (grid.j_index if grid is not None else rank))  # a row group shares its particles
+    eng0 = pls.basis.engine(j_local)  # workspaces (and the Gram cache, when used) are setup, like the reference's K_zx
+    gram_note = ("generated inside the kernels from the points (no N x M array)" if eng0.gram is None else
+                 f"cached in HBM ({eng0.gram.numel() * 8 / 1e9:.2f} GB, computed once at setup as the reference's K_zx is) and streamed")
     torch.cuda.synchronize()
     setup_s = time.perf_counter() - t_setup
 
@@ -509,7 +517,8 @@ def main():
     peak = peak_file or peak_live
     traffic = None
     try:
-        traffic_rec = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get(args.workload)
+        traffic_key = args.workload + ("" if eng0.gram is not None else "_generated")
+        traffic_rec = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get(traffic_key)
         if traffic_rec and not (args.n or args.j):
             traffic = traffic_rec["per_launch_bytes_mean"]
     except Exception:
@@ -521,8 +530,9 @@ def main():
         "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
         "traffic": traffic,
         "traffic_note": "DRAM bytes per launch (mean of the forward and backward roles) from one ncu --set full capture of this command, "
-                        "profiles/roofline_traffic.json; the kernel is FP64-pipe bound, traffic ~= the Dc chunk written / read once",
-        "kernel": "pls::gen_gemm_kernel (forward + backward roles; FP64 DMMA.8x8x4, no tcgen05 kind exists for f64)",
+                        "profiles/roofline_traffic.json; the kernel is FP64-pipe bound, traffic ~= the Dc chunk written / read once (+ the chunk's "
+                        "rows of the cached Gram read once)",
+        "kernel": "pls::gen_gemm_kernel (forward + backward roles; FP64 DMMA.8x8x4, no tcgen05 kind exists for f64); Gram " + gram_note,
         "algorithmic_flops_per_step": 4.0 * n * m * j,
         "algorithmic_flops_per_step_this_gpu": 4.0 * n_local * m * j_local,
         "per_role": {k: ksum[k] for k in ("forward", "backward") if k in ksum},
@@ -547,7 +557,7 @@ def main():
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if grid is not None else "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": workload["label"], "N": n, "D": workload["d"], "M": m, "M_k": m_k, "J_per_gpu": j_local,
-                   "J_global": j_global, "rows_per_gpu": n_local, "cost": workload["cost"], "step_size": eta, "lambda_min": lam_min,
+                   "J_global": j_global, "rows_per_gpu": n_local, "cost": workload["cost"], "step_size": eta, "lambda_min": lam_min, "gram": gram_note,
                    "noise": "Philox4x32-10 on device keyed on global (row, particle)", "parallelism": (f"grid {args.grid}: rows sharded x{grid.n_groups} (NCCL all-reduce of the M x J_local gradient per step), "
                                    f"particles sharded x{grid.j_groups}") if grid is not None else f"particle-sharded x{world}",
                    "l2": "per-step working set (Dc chunk 8 GiB written+read) exceeds the 126 MB L2; no flush needed",

@@ -147,15 +147,29 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, in
 }
 constexpr int KSRC_LINEAR = 0, KSRC_RBF = 1, KSRC_CACHED = 2;
 
-// streaming read-only loads of cached Gram values (each value is used once per tile: keep it out of L1)
-__device__ __forceinline__ double2 ldg_stream_v2(const double* ptr) {
+// L2 eviction policies.  The persistent forward CTAs that share a Gram row slab (the 16 column tiles of a row tile) drift
+// apart by several tile times while 8.6 GB of Dc stream through L2 per launch: the cached Gram values are loaded evict_last and
+// Dc is stored evict_first so that the slab survives until its last reader (ncu: DRAM reads of a forward launch 9.9 -> see
+// profiles/ncu_gen_gemm_cached_r01.txt).
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+// read-only loads of cached Gram values (each value is used once per tile: keep it out of L1, keep it in L2)
+__device__ __forceinline__ double2 ldg_stream_v2(const double* ptr, uint64_t pol) {
   double2 v;
-  asm("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(ptr));
+  asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(ptr), "l"(pol));
   return v;
 }
-__device__ __forceinline__ double ldg_stream(const double* ptr) {
+__device__ __forceinline__ double ldg_stream(const double* ptr, uint64_t pol) {
   double v;
-  asm("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(ptr));
+  asm("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(ptr), "l"(pol));
   return v;
 }
 
@@ -357,6 +371,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
   // Gram values of groups [g0, g0 + LA) of the point tile Pt; `first` = this thread's first reduction point of group g0,
   // counted from `begin` (points past the end of the reduction give 0)
   const double* kbase[RT];  // cached Gram: this thread's row (forward) / column (backward) of the tile, set per tile
+  const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
   auto gram_block = [&](const double* Pt, int g0, int first, double (&k)[LA][2][RT]) {
     if (KSRC == KSRC_CACHED) {
       // points first + 8 q and first + 8 q + 1 (from `begin`) of each of this thread's rows: forward = two adjacent columns of a
@@ -369,10 +384,10 @@ __global__ void __launch_bounds__(NTHREADS, 1)
         for (int h = 0; h < RT; ++h) {
           double2 v;
           if (BACKWARD) {
-            v.x = ldg_stream(kbase[h] + pt * p.ldk);
-            v.y = ldg_stream(kbase[h] + (pt + 1) * p.ldk);
+            v.x = ldg_stream(kbase[h] + pt * p.ldk, pol_keep);
+            v.y = ldg_stream(kbase[h] + (pt + 1) * p.ldk, pol_keep);
           } else {
-            v = ldg_stream_v2(kbase[h] + pt);
+            v = ldg_stream_v2(kbase[h] + pt, pol_keep);
           }
           // no masking: a point past the end of the reduction meets a zero row of the streamed matrix (the tensor map
           // zero-fills rows outside it), and the cache's padding is finite by contract.  A select here would be the first use
@@ -596,7 +611,9 @@ __global__ void __launch_bounds__(NTHREADS, 1)
           double* orow = p.out + r * p.ldo + j0;
           if (col + 3 < cols_here) {
             if (wide_store) {
-              asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(orow + col), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]) : "memory");
+              asm volatile("st.global.L2::cache_hint.v4.f64 [%0], {%1,%2,%3,%4}, %5;" ::"l"(orow + col), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]),
+                           "l"(pol_stream)
+                           : "memory");
             } else {
               double2* dst = reinterpret_cast<double2*>(orow + col);
               dst[0] = make_double2(v[0], v[1]);

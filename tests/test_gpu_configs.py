@@ -3,7 +3,8 @@
 C2 (N=10k, M=64, J=1024, Bernoulli) is checked in full against the oracle, including the selector.  C3 (N=100k, M=256,
 J=4096, Poisson f^2) and C4 (N=1M, D=8, M=1024, J=4096, Gaussian) are checked at FULL N and M on a slice of the particles
 (every term of the step is column-wise, orthonormal.py:151-158, so a slice of columns is the same computation) with the
-oracle's dense algebra evaluated in row chunks, plus size-independent properties on the full particle set.
+oracle's dense algebra evaluated in row chunks, plus size-independent properties on the full particle set.  Every config runs
+with the Gram generated inside the kernels and with the Gram cached in HBM (OrthonormalBasis(gram_cache=...)).
 """
 import math
 
@@ -56,7 +57,8 @@ def _curve_inputs(n, kind, seed=0):
     return x, y, g
 
 
-def test_config2_bernoulli_full(b200):
+@pytest.mark.parametrize("gram_cache", [False, True], ids=["generated", "cached"])
+def test_config2_bernoulli_full(b200, gram_cache):
     """C2: N=10 000, D=1, M=64, J=1024, BernoulliCost + Sigmoid.  The selector is compared for the first 24 pivots: a 1-D RBF
     Gram with lengthscale 0.5 on [-3, 3] has numerical rank ~30, beyond which every conditional variance is round-off of the
     1e-12 jitter and the pivot order is noise in the reference as well; the step uses bench.py's evenly spaced inducing points."""
@@ -76,7 +78,8 @@ def test_config2_bernoulli_full(b200):
     z = x[torch.linspace(0, n - 1, m).long()].clone()
     eig = torch.linalg.eigh((1 / m) * orc_kernel(z, z))
     orc = PLSOracle(OrthonormalBasisOracle(orc_kernel, z, x, eigenvalue_threshold=1e-10, eig=eig), Cost("bernoulli", y, Link("sigmoid")))
-    pls = b200.PLS(b200.OrthonormalBasis(b200.PLSKernel(kernel, z), z, x, eigenvalue_threshold=1e-10, eigendecomposition=eig, verbose=False),
+    pls = b200.PLS(b200.OrthonormalBasis(b200.PLSKernel(kernel, z), z, x, eigenvalue_threshold=1e-10, eigendecomposition=eig, verbose=False,
+                                         gram_cache=gram_cache),
                    costs.BernoulliCost(y, links.SigmoidLinkFunction()))
     m_k = orc.basis.approximation_dimension
     assert pls.basis.approximation_dimension == m_k
@@ -100,7 +103,8 @@ def _chunked_oracle_update(kernel, x, y, z, vt, lam, p, eta, xi, dcost, chunk=50
     return -eta * (vt.T @ g) - eta * (p / lam[:, None]) + math.sqrt(2 * eta) * xi, g
 
 
-def test_config3_poisson_full_rows(b200):
+@pytest.mark.parametrize("gram_cache", [False, True], ids=["generated", "cached"])
+def test_config3_poisson_full_rows(b200, gram_cache):
     """C3: N=100 000, D=1, M=256, PoissonCost + Square: a 192-particle slice at full N and M against the oracle, and the
     full J=4096 step's slice against the slice's own step (column independence)."""
     costs, links = _mods()
@@ -113,7 +117,8 @@ def test_config3_poisson_full_rows(b200):
     keep = lam > 1e-12
     lam_k, vec_k = lam[keep], vec[:, keep]
     vt = vec_k / torch.sqrt(lam_k.shape[0] * lam_k)  # orthonormal.py:63-68
-    basis = b200.OrthonormalBasis(b200.PLSKernel(kernel, z), z, x, eigenvalue_threshold=1e-12, eigendecomposition=(lam, vec), verbose=False)
+    basis = b200.OrthonormalBasis(b200.PLSKernel(kernel, z), z, x, eigenvalue_threshold=1e-12, eigendecomposition=(lam, vec), verbose=False,
+                                  gram_cache=gram_cache)
     assert rel_err(basis.scaled_eigenvectors, vt) < 1e-13
     pls = b200.PLS(basis, costs.PoissonCost(y, links.SquareLinkFunction()))
     m_k = lam_k.shape[0]
@@ -131,7 +136,8 @@ def test_config3_poisson_full_rows(b200):
     assert rel_err(got_full[:, :j_slice], want) < TOL
 
 
-def test_config4_gaussian_full_rows(b200):
+@pytest.mark.parametrize("gram_cache", [False, True], ids=["generated", "cached"])
+def test_config4_gaussian_full_rows(b200, gram_cache):
     """C4: N=1 000 000, D=8 ARD, M=1024, GaussianCost: a 64-particle slice at full N and M against the oracle's dense algebra
     (row-chunked on the CPU), then properties of the full J=4096 step: its slice equals the slice's own step, the Philox
     noise does not depend on how J is sharded, and the fused energy equals the cost-only forward."""
@@ -148,7 +154,7 @@ def test_config4_gaussian_full_rows(b200):
     keep = lam > 0.0
     lam_k, vec_k = lam[keep], vec[:, keep]
     vt = vec_k / torch.sqrt(lam_k.shape[0] * lam_k)
-    basis = b200.OrthonormalBasis(b200.PLSKernel(kernel, z), z, x, eigendecomposition=(lam, vec), verbose=False)
+    basis = b200.OrthonormalBasis(b200.PLSKernel(kernel, z), z, x, eigendecomposition=(lam, vec), verbose=False, gram_cache=gram_cache)
     pls = b200.PLS(basis, costs.GaussianCost(0.01, y, links.IdentityLinkFunction()))
     m_k = lam_k.shape[0]
     assert basis.approximation_dimension == m_k
