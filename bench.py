@@ -552,6 +552,34 @@ def main():
             library_bar = library_bar_sample(workload, pls, eta)
         except torch.OutOfMemoryError as exc:  # a reported comparison, never a reason to lose the line
             library_bar = {"unavailable": str(exc).splitlines()[0]}
+    shortcut = None
+    if world == 1 and workload["cost"] == "gaussian" and not args.no_cpu_baseline:
+        # informational, outside the timed region and NOT the headline: the opt-in Gaussian/identity re-association
+        # (LangevinEngine._normal_equations) that turns the step into M x M algebra after one N M^2 contraction
+        try:
+            pls.basis._gaussian_normal_equations = True
+            pls.basis._engines.clear()
+            q = particles.clone()
+            t0 = time.perf_counter()
+            pls.step_(q, eta, philox=(seed, 0, j_off))
+            torch.cuda.synchronize()
+            setup_ms = (time.perf_counter() - t0) * 1e3
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            for k in range(20):
+                pls.step_(q, eta, philox=(seed, 1 + k, j_off))
+            ev1.record()
+            torch.cuda.synchronize()
+            ms = ev0.elapsed_time(ev1) / 20
+            shortcut = {"value": j_local / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "setup_ms": setup_ms,
+                        "what": "opt-in OrthonormalBasis(gaussian_normal_equations=True): k(Z,X)k(X,Z)/s and k(Z,X)y/s formed once "
+                                "(setup_ms, 2 N M^2 flops), then 2 M^2 J flops per step; same particles to round-off "
+                                "(tests/test_gpu_configs.py::test_gaussian_normal_equations_shortcut); Gaussian cost only"}
+        except torch.OutOfMemoryError as exc:
+            shortcut = {"unavailable": str(exc).splitlines()[0]}
+        finally:
+            pls.basis._gaussian_normal_equations = False
+            pls.basis._engines.clear()
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, min_warmup),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if grid is not None else "weak", "vs_baseline": None, "dtype": "f64",
@@ -563,7 +591,7 @@ def main():
                    "l2": "per-step working set (Dc chunk 8 GiB written+read) exceeds the 126 MB L2; no flush needed",
                    "particles_finite": finite, "setup_s": setup_s},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
-        "library_bar": library_bar,
+        "library_bar": library_bar, "gaussian_normal_equations": shortcut,
     }
     emit(line)
     if dist is not None:

@@ -49,9 +49,12 @@ class LangevinEngine:
     def __init__(self, ctx: nat.Context, kernel_id: int, d: int, xa: torch.Tensor, za: torch.Tensor, vt: torch.Tensor,
                  inv_lambda: torch.Tensor, j: int, dc_budget_bytes: int = DEFAULT_DC_BUDGET,
                  gradient_reduce: Optional[Callable[[torch.Tensor], None]] = None,
-                 weights_fn: Optional[Callable[[torch.Tensor, torch.Tensor], None]] = None, gram: Optional[torch.Tensor] = None):
+                 weights_fn: Optional[Callable[[torch.Tensor, torch.Tensor], None]] = None, gram: Optional[torch.Tensor] = None,
+                 gaussian_normal_equations: bool = False):
         self.ctx, self.kernel_id, self.d = ctx, kernel_id, d
         self.gram = gram  # ops.gram_cache(...) of (xa, za) or None: Gram values loaded instead of generated
+        self.gaussian_normal_equations = gaussian_normal_equations  # opt-in, see _normal_equations()
+        self._neq = None  # (key, A' in Gram-cache layout, b', y^T y / (2 s))
         self.xa, self.za, self.vt, self.inv_lambda = xa, za, vt, inv_lambda
         self.n, self.m, self.m_k, self.j = xa.shape[0], za.shape[0], vt.shape[1], j
         self.gradient_reduce = gradient_reduce
@@ -67,6 +70,7 @@ class LangevinEngine:
         self.splits = ops.backward_splits(ctx, self.chunk_rows, self.m, j)
         self.gp = torch.zeros((self.splits, self.m, self.ldj), dtype=torch.float64, device=dev)
         self.cost_partial: Optional[torch.Tensor] = None  # (row tiles, ldj), allocated by the first gradient(with_cost=True)
+        self._neq_cost: Optional[torch.Tensor] = None
         self.tile_rows = 0
         self._zeros: Optional[torch.Tensor] = None
 
@@ -84,6 +88,9 @@ class LangevinEngine:
         """G' = k(Z, X) d_2 c(y, k(X, Z) V~ P)  -> (M, ldj) workspace view.  with_cost also leaves the per-row-tile cost
         sums of the SAME forward pass in self.cost_partial (the energy potential costs no second forward)."""
         self._weights(particles)
+        if self.gaussian_normal_equations and self._is_gaussian_identity(cost):
+            return self._gradient_normal_equations(cost, y, with_cost)
+        self._neq_cost = None
         if with_cost and self.cost_partial is None:
             self.tile_rows = ops.forward_tile_rows(self.ctx, self.j)
             tiles = sum((r1 - r0 + self.tile_rows - 1) // self.tile_rows for r0, r1 in self.chunks)
@@ -106,6 +113,62 @@ class LangevinEngine:
             self.gradient_reduce(self.gm)
         return self.gm
 
+    # ---- Gaussian / identity shortcut (opt-in) ---------------------------------------------------------------------------
+    @staticmethod
+    def _is_gaussian_identity(cost: nat.PlsCost) -> bool:
+        return cost.cost_id == nat.COST_GAUSSIAN and cost.link_id == nat.LINK_IDENTITY and cost.closed_form != 0
+
+    def _normal_equations(self, cost: nat.PlsCost, y: torch.Tensor):
+        """For the Gaussian cost with the identity link the gradient is LINEAR in W:
+               G' = k(Z,X) (k(X,Z) W - y) / s = A' W - b' 1^T,   A' = k(Z,X) k(X,Z) / s  (M x M),  b' = k(Z,X) y / s  (M),
+        and the cost sums are quadratic: sum_n (F_nj - y_n)^2 / (2 s) = 1/2 w_j^T A' w_j - b'^T w_j + y^T y / (2 s).
+        A' and b' are formed ONCE (one backward contraction with the Gram as the streamed matrix: 2 N M^2 flops), after which a
+        step costs 2 M^2 J flops instead of 4 N M J.  This is a re-association of the reference's algebra
+        (orthonormal.py:98-108,151-158 with costs/gaussian.py:75-88), exact up to round-off, NOT the general path: bench.py's
+        headline never uses it."""
+        key = (y.data_ptr(), y.shape[0], float(cost.observation_noise))
+        if self._neq is not None and self._neq[0] == key:
+            return self._neq
+        ctx, m, dev = self.ctx, self.m, self.xa.device
+        s_obs = float(cost.observation_noise)
+        a_pad = torch.zeros((int(ctx.lib.pls_gram_cache_rows(m)), int(ctx.lib.pls_gram_cache_ld(m))), dtype=torch.float64, device=dev)
+        ldm = a_pad.shape[1]
+        rows = 65536
+        splits = ops.backward_splits(ctx, min(rows, self.n), m, m)
+        gp_a = torch.zeros((splits, m, ldm), dtype=torch.float64, device=dev)
+        gp_b = torch.zeros((splits, m, 16), dtype=torch.float64, device=dev)
+        y2 = torch.zeros((self.n, 16), dtype=torch.float64, device=dev)  # y as column 0 of a one-block-wide streamed matrix
+        y2[:, 0] = y
+        for ci, r0 in enumerate(range(0, self.n, rows)):
+            r1 = min(self.n, r0 + rows)
+            k = self.gram[r0:] if self.gram is not None else ops.gram_cache(ctx, self.kernel_id, self.xa[r0:r1], self.za, self.d)
+            # the Gram chunk is both the (loaded) left operand and the streamed matrix: Gp += k(Z, X_c) k(X_c, Z)
+            ops.backward(ctx, self.kernel_id, self.za, self.xa[r0:r1], self.d, k[: r1 - r0], m, gp_a, splits, accumulate=ci > 0, gram=k)
+            ops.backward(ctx, self.kernel_id, self.za, self.xa[r0:r1], self.d, y2[r0:r1], 1, gp_b, splits, accumulate=ci > 0, gram=k)
+        a = torch.zeros((m, ldm), dtype=torch.float64, device=dev)
+        b2 = torch.zeros((m, 16), dtype=torch.float64, device=dev)
+        ops.reduce_splits(ctx, gp_a, m, a)
+        ops.reduce_splits(ctx, gp_b, 1, b2)
+        b = b2[:, 0].contiguous()
+        yy = (y * y).sum().reshape(1)
+        if self.gradient_reduce is not None:  # rows sharded: A', b' and y^T y are sums over the row group -- reduced once, not per step
+            self.gradient_reduce(a)
+            self.gradient_reduce(b)
+            self.gradient_reduce(yy)
+        a_pad[:m, :m] = a[:, :m] / s_obs
+        self._neq = (key, a_pad, (b / s_obs).contiguous(), yy / (2.0 * s_obs))
+        return self._neq
+
+    def _gradient_normal_equations(self, cost: nat.PlsCost, y: torch.Tensor, with_cost: bool) -> torch.Tensor:
+        _, a_pad, b, yy = self._normal_equations(cost, y)
+        # G' = A' W through the cached-Gram forward kernel (A' plays the Gram: M "training rows" x M inducing points)
+        ops.forward(self.ctx, self.kernel_id, self.za, self.za, self.d, self.w, self.j, nat.EPI_PREDICTION, self.gm, gram=a_pad)
+        g = self.gm[:, : self.j]
+        w = self.w[:, : self.j]
+        self._neq_cost = (0.5 * (w * g).sum(0) - b @ w + yy) if with_cost else None  # before b' is subtracted: g = A' W
+        g.sub_(b[:, None])
+        return self.gm
+
     def step(self, particles: torch.Tensor, eta: float, cost: nat.PlsCost, y: torch.Tensor, out: torch.Tensor,
              noise_mode: int, xi: Optional[torch.Tensor] = None, seed: int = 0, step_index: int = 0,
              j_global_offset: int = 0, in_place: bool = False) -> torch.Tensor:
@@ -117,6 +180,8 @@ class LangevinEngine:
         """One forward + backward: leaves G' in self.gm and returns the per-particle energy c_j + 1/2 sum_m P_mj^2 / lambda_m
         of `particles` (J,) (PLS.calculate_energy_potential before its mean, orthonormal.py:110-126)."""
         self.gradient(particles, cost, y, with_cost=True)
+        if self._neq_cost is not None:  # Gaussian shortcut: the cost sums are complete on every rank already
+            return ops.energy_terms(self.ctx, self._neq_cost.reshape(1, -1).contiguous(), self.j, particles, self.inv_lambda)
         if self.gradient_reduce is None:
             return ops.energy_terms(self.ctx, self.cost_partial, self.j, particles, self.inv_lambda)
         # rows are sharded: the cost sums are partial over this rank's rows (summed over the row group), the prior term is not

@@ -31,6 +31,8 @@ class OrthonormalBasis(PLSBasis):
       dc_budget_bytes     size cap of the d_2 c row-chunk workspace of the fused step
       gradient_reduce     callable applied in place to the (M, J) gradient before the update (NCCL all-reduce when
                           the training rows are sharded across GPUs)
+      gaussian_normal_equations   opt-in: with GaussianCost + identity link, form k(Z,X)k(X,Z)/s and k(Z,X)y/s once and run every
+                          step in M x M algebra (2 M^2 J flops instead of 4 N M J); see LangevinEngine._normal_equations
       gram_cache          "auto" (default) / True / False: keep k(X, Z) resident in HBM, as the reference does
                           (orthonormal.py:36-41), and stream it instead of regenerating it in the kernels; "auto" does so
                           when it fits comfortably (engine.want_gram_cache)
@@ -40,10 +42,11 @@ class OrthonormalBasis(PLSBasis):
                  additional_predictive_noise_distribution: Optional[torch.distributions.Distribution] = None, *,
                  eigendecomposition: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, eigh_device: str = "cpu",
                  dc_budget_bytes: int = DEFAULT_DC_BUDGET, gradient_reduce=None, verbose: bool = True,
-                 gram_cache="auto"):
+                 gram_cache="auto", gaussian_normal_equations: bool = False):
         super().__init__(additional_predictive_noise_distribution=additional_predictive_noise_distribution)
         self.kernel = kernel
         self._gram_cache_mode, self._gram = gram_cache, None
+        self._gaussian_normal_equations = gaussian_normal_equations
         self.ctx = nat.context()
         dev = torch.device("cuda", self.ctx.device_index)
         self.x_induce = ops.as_device_f64(x_induce if x_induce.dim() > 1 else x_induce.unsqueeze(-1), dev)  # (M, D)
@@ -104,7 +107,8 @@ class OrthonormalBasis(PLSBasis):
                 self._gram = ops.gram_cache(self.ctx, self._spec.kernel_id, self._xa, self._za, self._d)  # k(X, Z), once
             eng = LangevinEngine(self.ctx, self._spec.kernel_id, self._d, self._xa, self._za, self.scaled_eigenvectors,
                                  self._inv_lambda, number_of_particles, dc_budget_bytes=self._dc_budget,
-                                 gradient_reduce=self._gradient_reduce, gram=self._gram)
+                                 gradient_reduce=self._gradient_reduce, gram=self._gram,
+                                 gaussian_normal_equations=self._gaussian_normal_equations)
             self._engines[number_of_particles] = eng
         return eng
 

@@ -186,3 +186,47 @@ def test_config4_gaussian_full_rows(b200, gram_cache):
     e_plain = pls.calculate_energy_potential(p_full)
     assert abs(e_fused - e_plain) <= 1e-12 * abs(e_plain)
     assert np.isfinite(e_plain)
+
+
+@pytest.mark.parametrize("gram_cache", [False, True], ids=["generated", "cached"])
+def test_gaussian_normal_equations_shortcut(b200, gram_cache):
+    """Opt-in Gaussian / identity shortcut (LangevinEngine._normal_equations: A' = k(Z,X)k(X,Z)/s and b' = k(Z,X)y/s formed once,
+    every step in M x M algebra): update and energy against the oracle, then 25 in-place steps and the fused training epoch
+    against the general path on a larger problem."""
+    costs, links = _mods()
+    from projected_langevin_sampling_b200.trainers import train_pls
+
+    g = torch.Generator().manual_seed(5)
+    n, d, m, j = 30_000, 4, 96, 300
+    x = torch.randn(n, d, generator=g, dtype=torch.float64)
+    y = torch.sin(x.sum(1)) + 0.1 * torch.randn(n, generator=g, dtype=torch.float64)
+    z = x[:m].clone()
+    ls = torch.tensor([1.6, 2.0, 2.4, 2.8], dtype=torch.float64)
+    orc_kernel = RBFScaleKernel(ls, 1.2)
+    kernel = b200.ScaleKernel(b200.RBFKernel(ard_num_dims=d, lengthscale=ls), outputscale=1.2)
+    eig = torch.linalg.eigh((1 / m) * orc_kernel(z, z))
+
+    def make(shortcut):
+        basis = b200.OrthonormalBasis(b200.PLSKernel(kernel, z), z, x, eigenvalue_threshold=1e-10, eigendecomposition=eig, verbose=False,
+                                      gram_cache=gram_cache, gaussian_normal_equations=shortcut)
+        return b200.PLS(basis, costs.GaussianCost(0.05, y, links.IdentityLinkFunction()))
+
+    fast, general = make(True), make(False)
+    orc = PLSOracle(OrthonormalBasisOracle(orc_kernel, z, x, eigenvalue_threshold=1e-10, eig=eig), Cost("gaussian", y, Link("identity"), observation_noise=0.05))
+    m_k = orc.basis.approximation_dimension
+    p = torch.randn(m_k, j, generator=g, dtype=torch.float64)
+    xi = torch.randn(m_k, j, generator=g, dtype=torch.float64)
+    want = orc.calculate_particle_update(p, 1e-6, noise=xi)
+    assert rel_err(fast.calculate_particle_update(p.cuda(), 1e-6, noise=xi), want) < TOL
+    assert fast.basis.engine(j)._neq is not None and general.basis.engine(j)._neq is None
+    pf, pg = p.cuda().clone(), p.cuda().clone()
+    for s in range(25):
+        fast.step_(pf, 2e-6, philox=(3, s, 0))
+        general.step_(pg, 2e-6, philox=(3, s, 0))
+    assert rel_err(pf, pg) < TOL
+    e_fast = fast.basis.engine(j).energy_and_gradient(pf, fast.cost.native(), fast.cost.y_device()).mean().item()
+    e_want = orc.calculate_energy_potential(pg.cpu())
+    assert abs(e_fast - e_want) <= TOL * abs(e_want)
+    _, ef = train_pls(fast, pf.clone(), number_of_epochs=6, step_size=1e-6, early_stopper_patience=1e9, philox_seed=11)
+    _, eg = train_pls(general, pf.clone(), number_of_epochs=6, step_size=1e-6, early_stopper_patience=1e9, philox_seed=11)
+    assert len(ef) == len(eg) == 6 and max(abs(a - b) / abs(b) for a, b in zip(ef, eg)) < TOL
