@@ -13,8 +13,9 @@ One step (reference: PLS.calculate_particle_update, src/projected_langevin_sampl
 
 The N x J prediction matrix is never materialised; the only N x J intermediate is the Dc chunk (`dc_budget_bytes`, default
 8 GiB), written and read once per step (~2 % of the step time at the headline shape).  The N x M Gram is generated inside the
-kernels from the points, or -- `gram_cache`, when N x M doubles fit comfortably (the reference keeps k(Z, X) for the whole run,
-orthonormal.py:36-41) -- computed once and streamed, which takes the exponent work off the FP64 pipe.
+kernels from the points (default: nothing N x M in memory) or -- opt-in `gram_cache`, when N x M doubles fit (the reference
+keeps k(Z, X) for the whole run, orthonormal.py:36-41) -- computed once and streamed, which takes the exponent work off the
+FP64 pipe (+9 % at the headline shape for 8.2 GB).
 """
 from __future__ import annotations
 
@@ -32,10 +33,11 @@ DEFAULT_GRAM_CACHE_BYTES = 24 << 30
 
 
 def want_gram_cache(mode: Union[bool, str, None], ctx: nat.Context, n: int, m: int, device: torch.device) -> bool:
-    """Policy for keeping k(X, Z) resident.  mode: True / "on", False / "off", or "auto" (default; the environment variable
-    PLS_B200_GRAM_CACHE overrides it): cache when it takes at most PLS_B200_GRAM_CACHE_BYTES (24 GiB) and a third of the free
-    device memory."""
-    mode = os.environ.get("PLS_B200_GRAM_CACHE", mode if mode is not None else "auto")
+    """Policy for keeping k(X, Z) resident.  mode: False / "off" (the default: Gram tiles are regenerated inside the kernels and
+    nothing N x M is ever in memory, as BASELINE.json's north_star specifies), True / "on", or "auto": cache when it takes at
+    most PLS_B200_GRAM_CACHE_BYTES (24 GiB) and a third of the free device memory.  The environment variable
+    PLS_B200_GRAM_CACHE overrides the argument."""
+    mode = os.environ.get("PLS_B200_GRAM_CACHE", mode if mode is not None else False)
     if mode in (True, "on", "1", "true"):
         return True
     if mode in (False, "off", "0", "false"):

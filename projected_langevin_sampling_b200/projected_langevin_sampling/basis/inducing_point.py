@@ -26,7 +26,7 @@ from .base import PLSBasis
 class InducingPointBasis(PLSBasis):
     def __init__(self, kernel, x_induce: torch.Tensor, y_induce: torch.Tensor, x_train: torch.Tensor,
                  additional_predictive_noise_distribution: Optional[torch.distributions.Distribution] = None, *,
-                 dc_budget_bytes: int = DEFAULT_DC_BUDGET, gradient_reduce=None, gram_cache="auto"):
+                 dc_budget_bytes: int = DEFAULT_DC_BUDGET, gradient_reduce=None, gram_cache=False):
         super().__init__(additional_predictive_noise_distribution=additional_predictive_noise_distribution)
         self.kernel = kernel
         self._gram_cache_mode, self._gram = gram_cache, None  # as OrthonormalBasis

@@ -33,16 +33,16 @@ class OrthonormalBasis(PLSBasis):
                           the training rows are sharded across GPUs)
       gaussian_normal_equations   opt-in: with GaussianCost + identity link, form k(Z,X)k(X,Z)/s and k(Z,X)y/s once and run every
                           step in M x M algebra (2 M^2 J flops instead of 4 N M J); see LangevinEngine._normal_equations
-      gram_cache          "auto" (default) / True / False: keep k(X, Z) resident in HBM, as the reference does
-                          (orthonormal.py:36-41), and stream it instead of regenerating it in the kernels; "auto" does so
-                          when it fits comfortably (engine.want_gram_cache)
+      gram_cache          False (default: Gram tiles regenerated inside the kernels, nothing N x M in memory) / True / "auto":
+                          keep k(X, Z) resident in HBM, as the reference does (orthonormal.py:36-41), and stream it;
+                          "auto" does so when it fits comfortably (engine.want_gram_cache)
     """
 
     def __init__(self, kernel, x_induce: torch.Tensor, x_train: torch.Tensor, eigenvalue_threshold: float = 0.0,
                  additional_predictive_noise_distribution: Optional[torch.distributions.Distribution] = None, *,
                  eigendecomposition: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, eigh_device: str = "cpu",
                  dc_budget_bytes: int = DEFAULT_DC_BUDGET, gradient_reduce=None, verbose: bool = True,
-                 gram_cache="auto", gaussian_normal_equations: bool = False):
+                 gram_cache=False, gaussian_normal_equations: bool = False):
         super().__init__(additional_predictive_noise_distribution=additional_predictive_noise_distribution)
         self.kernel = kernel
         self._gram_cache_mode, self._gram = gram_cache, None
