@@ -1,4 +1,5 @@
-// The hot kernel of the PLS Langevin step: a GEMM whose A operand is GENERATED, never stored.
+// The hot kernel of the PLS Langevin step: a GEMM whose A operand is GENERATED, never stored (default), or streamed from a
+// caller-kept Gram (opt-in).
 //
 //     C[r][j] (+)= sum_k  kappa(row_r, red_k) * B[k][j]
 //
@@ -26,8 +27,12 @@
 //     bank-conflict free without padding (lane (g,t) reads 16-byte chunk g ^ (row & 7) of row 2t [+1]).  The
 //     reduction-point rows follow with one plain bulk copy.  3-stage full-barrier pipeline; a stage is refilled by the
 //     LAST warp to release it (atomic counter), so no warp ever waits to issue a copy.
-//   * the loop over 8-point groups is flat and branch-free (kernel kind is a template parameter) so ptxas can interleave
-//     the exponent chain of the NEXT k4 step with the 32 DMMAs of the current one.
+//   * the loop over 8-point groups is flat and branch-free (the Gram source is a template parameter) and the Gram values of
+//     a whole 32-point stage are produced one stage ahead, in two register sets that swap roles (never copied), so ptxas
+//     interleaves the 8 independent exponent chains of the NEXT stage with the DMMAs of the current one.
+//   * optional KSRC_CACHED variant (pls_*_cached_f64): the caller keeps k(X, Z) in HBM and the kernels LOAD their fragment
+//     values (L2::evict_last, one stage ahead) instead of generating them -- the FP64 pipe then runs nothing but the
+//     contraction.  The default path generates: nothing N x M is ever in memory.
 #pragma once
 #include <cuda.h>
 
