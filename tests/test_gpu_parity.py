@@ -696,18 +696,19 @@ def test_ipb_step_matches_oracle_at_size(b200):
         assert torch.linalg.cond(orc_basis.base_gram_induce) < 1e3
         orc = PLSOracle(orc_basis, Cost("student_t", y, Link("identity"), degrees_of_freedom=5.0, scale=0.8))
         kernel = b200.ScaleKernel(b200.RBFKernel(ard_num_dims=d, lengthscale=ls), outputscale=1.1)
-        basis = b200.InducingPointBasis(b200.PLSKernel(kernel, z), z, y_induce, x, dc_budget_bytes=512 * 70 * 8)
-        pls = b200.PLS(basis, costs.StudentTCost(5.0, y, links.IdentityLinkFunction(), scale=0.8))
         p = y_induce[:, None] + 0.3 * torch.randn(m, j, generator=g, dtype=torch.float64)
         zn = torch.randn(m, j, generator=g, dtype=torch.float64)
         want = orc.calculate_particle_update(p, 2e-3, noise=zn)
-        assert rel_err(pls.calculate_particle_update(p.cuda(), 2e-3, noise=zn), want) < TOL
-        assert len(basis.engine(j).chunks) > 1
         e_want = orc.calculate_energy_potential(p)
-        assert abs(pls.calculate_energy_potential(p.cuda()) - e_want) <= TOL * abs(e_want)
-        q = p.cuda().clone()
-        basis.fused_particle_update(q, pls.cost, 2e-3, noise=zn, in_place=True)
-        assert rel_err(q, p + want) < TOL
+        for gram_cache in (False, True):  # Gram tiles generated in the kernels / k(X, Z) kept in HBM and streamed
+            basis = b200.InducingPointBasis(b200.PLSKernel(kernel, z), z, y_induce, x, dc_budget_bytes=512 * 70 * 8, gram_cache=gram_cache)
+            pls = b200.PLS(basis, costs.StudentTCost(5.0, y, links.IdentityLinkFunction(), scale=0.8))
+            assert rel_err(pls.calculate_particle_update(p.cuda(), 2e-3, noise=zn), want) < TOL
+            assert len(basis.engine(j).chunks) > 1 and (basis.engine(j).gram is not None) == gram_cache
+            assert abs(pls.calculate_energy_potential(p.cuda()) - e_want) <= TOL * abs(e_want)
+            q = p.cuda().clone()
+            basis.fused_particle_update(q, pls.cost, 2e-3, noise=zn, in_place=True)
+            assert rel_err(q, p + want) < TOL
     finally:
         torch.set_default_dtype(torch.float32)
 
