@@ -362,7 +362,7 @@ def main():
     ap.add_argument("--grid", type=str, default=None,
                     help="RxC = row shards x particle shards of ONE problem (strong scaling; needs R*C == world). Default: every GPU "
                          "advances its own J particles against replicated data (weak scaling in J, no communication)")
-    ap.add_argument("--gram", type=str, default="generated", choices=["auto", "cached", "generated"],
+    ap.add_argument("--gram", type=str, default="generated", choices=["auto", "cached", "staged", "generated"],
                     help="generated (default, the path BASELINE.json's north_star names: Gram tiles recomputed inside the kernels, "
                          "nothing N x M in memory) or cached (opt-in: k(X, Z) kept resident in HBM and streamed -- C4: 8.2 GB per "
                          "GPU); auto caches when it fits comfortably (engine.want_gram_cache).  At N = 1 the default run also "
@@ -399,7 +399,7 @@ def main():
     ctx = _native.context()
     t_setup = time.perf_counter()
     x, y, z, ls, outputscale = synth(workload)
-    gram_mode = {"auto": "auto", "cached": True, "generated": False}[args.gram]
+    gram_mode = {"auto": "auto", "cached": True, "staged": "staged", "generated": False}[args.gram]
     grid = None
     if args.grid:
         from projected_langevin_sampling_b200.distributed import GridPlacement, gradient_allreduce, make_row_group
@@ -422,9 +422,12 @@ def main():
     eta = 1e-9 if workload["cost"] == "gaussian" else 1e-6
     particles = pls.initialise_particles(j_local, seed=1000 + (grid.j_index if grid is not None else rank))  # a row group shares its particles
     eng0 = pls.basis.engine(j_local)  # workspaces (and the Gram cache, when used) are setup, like the reference's K_zx
-    gram_note = ("generated inside the kernels from the points (no N x M array)" if eng0.gram is None else
+    gram_note = ("re-formed every step into a chunk-sized staging buffer (%.2f GB; no N x M array)" % (eng0.kstage.numel() * 8 / 1e9)
+                 if eng0.kstage is not None else
+                 "generated inside the kernels from the points (no N x M array)" if eng0.gram is None else
                  f"cached in HBM ({eng0.gram.numel() * 8 / 1e9:.2f} GB, computed once at setup as the reference's K_zx is) and streamed")
     gram_is_cached = eng0.gram is not None
+    gram_key = "_cached" if gram_is_cached else ("_staged" if eng0.kstage is not None else "")
     del eng0
     torch.cuda.synchronize()
     setup_s = time.perf_counter() - t_setup
@@ -523,7 +526,7 @@ def main():
     traffic_all = {}
     try:
         traffic_all = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
-        traffic_rec = traffic_all.get(args.workload + ("_cached" if gram_is_cached else ""))
+        traffic_rec = traffic_all.get(args.workload + gram_key)
         if traffic_rec and not (args.n or args.j):
             traffic = traffic_rec["per_launch_bytes_mean"]
     except Exception:
@@ -557,43 +560,52 @@ def main():
             library_bar = library_bar_sample(workload, pls, eta)
         except torch.OutOfMemoryError as exc:  # a reported comparison, never a reason to lose the line
             library_bar = {"unavailable": str(exc).splitlines()[0]}
-    cached = None
-    if world == 1 and not gram_is_cached and not args.no_cpu_baseline:
-        # informational second measurement, after and outside the headline's timed region: the same steps with the opt-in Gram
-        # cache (OrthonormalBasis(gram_cache=True): k(X, Z) computed once, kept in HBM and streamed by the same kernels)
-        try:
-            pls.basis._gram_cache_mode = True
-            pls.basis._engines.clear()
-            q = particles.clone()
-            for k in range(2):
-                pls.step_(q, eta, philox=(seed, k, j_off))
-            torch.cuda.synchronize()
-            timer.records = []
-            timer.enabled = True
-            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            ev0.record()
-            for k in range(args.steps):
-                pls.step_(q, eta, philox=(seed, 2 + k, j_off))
-            ev1.record()
-            torch.cuda.synchronize()
-            timer.enabled = False
-            ms_c = ev0.elapsed_time(ev1) / args.steps
-            ks_c = timer.summary()
-            eng_c = pls.basis.engine(j_local)
-            cached = {"value": j_local / (ms_c * 1e-3), "unit": UNIT, "ms_per_step": ms_c, "steps": args.steps,
-                      "tflops": ks_c["both"]["tflops"], "frac": ks_c["both"]["tflops"] / peak if peak else None,
-                      "per_role_tflops": {k: ks_c[k]["tflops"] for k in ("forward", "backward") if k in ks_c},
-                      "gram_bytes": int(eng_c.gram.numel() * 8) if eng_c.gram is not None else 0,
-                      "traffic": (traffic_all.get(args.workload + "_cached") or {}).get("per_launch_bytes_mean") if not (args.n or args.j) else None,
-                      "what": "same launch sequence with OrthonormalBasis(gram_cache=True): k(X, Z) kept resident in HBM (as the reference "
-                              "keeps K_zx) and loaded by pls_*_cached_f64 instead of regenerated; opt-in because north_star specifies "
-                              "on-the-fly Gram tiles"}
-        except torch.OutOfMemoryError as exc:
-            cached = {"unavailable": str(exc).splitlines()[0]}
-        finally:
-            pls.basis._gram_cache_mode = False
-            pls.basis._engines.clear()
-            torch.cuda.empty_cache()
+    extras = {"gram_cached": None, "gram_staged": None}
+    if world == 1 and gram_mode is False and not args.no_cpu_baseline:
+        # informational measurements, after and outside the headline's timed region: the same steps with the two opt-in Gram
+        # modes -- cached (k(X, Z) computed once and kept in HBM, as the reference keeps K_zx) and staged (k(X_c, Z) re-formed
+        # every step into one chunk-sized buffer shared by the chunk's forward and backward launches; nothing N x M kept)
+        notes = {"gram_cached": "OrthonormalBasis(gram_cache=True): k(X, Z) kept resident in HBM and loaded by pls_*_cached_f64 instead of "
+                                "regenerated; opt-in because north_star specifies on-the-fly Gram tiles",
+                 "gram_staged": "OrthonormalBasis(gram_cache='staged'): nothing N x M kept; every step pls_gram_fill_f64 re-forms k(X_c, Z) "
+                                "for the row chunk in flight into one chunk-sized buffer that the chunk's forward and backward launches "
+                                "stream (instead of each of their J/256 column tiles regenerating it)"}
+        for key, mode in (("gram_cached", True), ("gram_staged", "staged")):
+            try:
+                pls.basis._gram_cache_mode, pls.basis._gram = mode, None
+                pls.basis._engines.clear()
+                q = particles.clone()
+                for k in range(2):
+                    pls.step_(q, eta, philox=(seed, k, j_off))
+                torch.cuda.synchronize()
+                timer.records = []
+                timer.enabled = True
+                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ev0.record()
+                for k in range(args.steps):
+                    pls.step_(q, eta, philox=(seed, 2 + k, j_off))
+                ev1.record()
+                torch.cuda.synchronize()
+                timer.enabled = False
+                ms_c = ev0.elapsed_time(ev1) / args.steps
+                ks_c = timer.summary()
+                eng_c = pls.basis.engine(j_local)
+                buf = eng_c.gram if eng_c.gram is not None else eng_c.kstage
+                extras[key] = {"value": j_local / (ms_c * 1e-3), "unit": UNIT, "ms_per_step": ms_c, "steps": args.steps,
+                               "tflops": ks_c["both"]["tflops"], "frac": ks_c["both"]["tflops"] / peak if peak else None,
+                               "step_tflops": 4.0 * n * m * j_local / (ms_c * 1e-3) * 1e-12,
+                               "per_role_tflops": {k: ks_c[k]["tflops"] for k in ("forward", "backward") if k in ks_c},
+                               "gram_bytes": int(buf.numel() * 8) if buf is not None else 0,
+                               "traffic": ((traffic_all.get(args.workload + "_cached") or {}).get("per_launch_bytes_mean")
+                                           if key == "gram_cached" and not (args.n or args.j) else None),
+                               "what": "same launch sequence with " + notes[key]}
+                del eng_c, buf
+            except torch.OutOfMemoryError as exc:
+                extras[key] = {"unavailable": str(exc).splitlines()[0]}
+            finally:
+                pls.basis._gram_cache_mode, pls.basis._gram = False, None
+                pls.basis._engines.clear()
+                torch.cuda.empty_cache()
     shortcut = None
     if world == 1 and workload["cost"] == "gaussian" and not args.no_cpu_baseline:
         # informational, outside the timed region and NOT the headline: the opt-in Gaussian/identity re-association
@@ -633,7 +645,8 @@ def main():
                    "l2": "per-step working set (Dc chunk 8 GiB written+read) exceeds the 126 MB L2; no flush needed",
                    "particles_finite": finite, "setup_s": setup_s},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
-        "library_bar": library_bar, "gram_cached": cached, "gaussian_normal_equations": shortcut,
+        "library_bar": library_bar, "gram_cached": extras["gram_cached"], "gram_staged": extras["gram_staged"],
+        "gaussian_normal_equations": shortcut,
     }
     emit(line)
     if dist is not None:

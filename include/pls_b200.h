@@ -168,6 +168,10 @@ int pls_backward_f64(pls_ctx* ctx, int kernel_id, const double* za, int64_t m, c
  * at any row of a larger cache (row chunks).  Arguments and results are otherwise those of pls_forward_f64,
  * pls_forward_step_f64 and pls_backward_f64 (equal to round-off: pls_gram_f64's values and the kernels' generated ones are
  * two evaluations of the same exponent, each within an ulp). */
+/* pls_gram_f64 at stream speed for filling such a buffer (whole cache, or a row chunk re-filled every step): same arguments,
+ * the exp is the contraction kernels' own table-driven routine (within 2 ulp of pls_gram_f64's); at most 2 097 120 rows a call. */
+int pls_gram_fill_f64(pls_ctx* ctx, int kernel_id, const double* rows_aug, int64_t n_rows, const double* cols_aug,
+                      int64_t n_cols, int d, double* out, int64_t ldo, void* stream);
 int64_t pls_gram_cache_ld(int64_t m);
 int64_t pls_gram_cache_rows(int64_t n);
 int pls_forward_cached_f64(pls_ctx* ctx, const double* k, int64_t ldk, int64_t n, int64_t m, const double* w, int64_t ldw,

@@ -70,6 +70,7 @@ SIGNATURES = {
     "pls_forward_f64": (_int, [_vp, _int, _vp, _i64, _vp, _i64, _int, _vp, _i64, _i64, _int, _costp, _vp, _vp, _i64, _vp]),
     "pls_forward_step_f64": (_int, [_vp, _int, _vp, _i64, _vp, _i64, _int, _vp, _i64, _i64, _costp, _vp, _vp, _i64, _vp, _i64, _vp]),
     "pls_backward_f64": (_int, [_vp, _int, _vp, _i64, _vp, _i64, _int, _vp, _i64, _i64, _vp, _i64, _int, _int, _vp]),
+    "pls_gram_fill_f64": (_int, [_vp, _int, _vp, _i64, _vp, _i64, _int, _vp, _i64, _vp]),
     "pls_gram_cache_ld": (_i64, [_i64]),
     "pls_gram_cache_rows": (_i64, [_i64]),
     "pls_forward_cached_f64": (_int, [_vp, _vp, _i64, _i64, _i64, _vp, _i64, _i64, _int, _costp, _vp, _vp, _i64, _vp]),

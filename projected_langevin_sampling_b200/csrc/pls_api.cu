@@ -148,6 +148,18 @@ int pls_gram_f64(pls_ctx* ctx, int kernel_id, const double* rows_aug, int64_t n_
                     "pls_gram_f64");
 }
 
+int pls_gram_fill_f64(pls_ctx* ctx, int kernel_id, const double* rows_aug, int64_t n_rows, const double* cols_aug,
+                      int64_t n_cols, int d, double* out, int64_t ldo, void* stream) {
+  if (!ctx) return 1;
+  if (check_kernel(ctx, kernel_id, d)) return 1;
+  if (n_rows < 0 || n_cols < 0 || ldo < n_cols || !out) return fail(ctx, "pls_gram_fill_f64: bad arguments");
+  if (n_rows > 65535LL * 32) return fail(ctx, "pls_gram_fill_f64: at most %lld rows per call", 65535LL * 32);
+  return check_cuda(ctx,
+                    pls::launch_gram_fill(kernel_id, rows_aug, n_rows, cols_aug, n_cols, d, pls::point_stride(d), out, ldo,
+                                          (cudaStream_t)stream),
+                    "pls_gram_fill_f64");
+}
+
 int pls_gemm_f64(pls_ctx* ctx, int trans_a, const double* a, int64_t lda, const double* b, int64_t ldb, double* c,
                  int64_t ldc, int64_t rows, int64_t j, int64_t k, void* stream) {
   if (!ctx) return 1;

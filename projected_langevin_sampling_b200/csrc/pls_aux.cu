@@ -71,6 +71,66 @@ cudaError_t launch_gram(int kernel_id, const double* ra, int64_t nr, const doubl
   return cudaGetLastError();
 }
 
+// The same Gram at stream speed, for the buffers the pls_*_cached_f64 kernels read (cache or per-chunk staging): one CTA =
+// 32 rows x 128 columns; each thread keeps ITS column point in registers, the rows are staged in shared memory and broadcast,
+// four rows are in flight per thread, the exp is the contraction kernels' own table-driven routine (<= 2 ulp).
+constexpr int GF_ROWS = 32, GF_COLS = 128;
+template <int NK>  // (d + 2) rounded up to a multiple of 4
+__global__ void __launch_bounds__(GF_COLS) gram_fill_kernel(int kernel_id, const double* __restrict__ ra, int64_t nr,
+                                                            const double* __restrict__ ca, int64_t nc, int d, int sp,
+                                                            double* __restrict__ out, int64_t ldo) {
+  __shared__ double srow[GF_ROWS * NK];
+  __shared__ double tbl[64];
+  const int tid = threadIdx.x;
+  const int64_t c = (int64_t)blockIdx.x * GF_COLS + tid;
+  const int64_t r0 = (int64_t)blockIdx.y * GF_ROWS;
+  const int nrows = (int)((nr - r0 < GF_ROWS) ? (nr - r0) : GF_ROWS);
+  if (tid < 64) tbl[tid] = kExp2Table[tid];
+  // rows: coordinates, then the two affine entries, zero padded to NK; rows past the end are zeros
+  for (int i = tid; i < GF_ROWS * NK; i += GF_COLS) {
+    const int r = i / NK, k = i - r * NK;
+    srow[i] = (r < nrows && k < d + 2) ? ra[(r0 + r) * sp + k] : 0.0;
+  }
+  // this thread's column point, with its two affine entries swapped so that s = sum_k row[k] * col[k]  (gram_kernel above)
+  double bv[NK];
+#pragma unroll
+  for (int k = 0; k < NK; ++k) {
+    const int src = (k < d) ? k : ((k == d) ? d + 1 : d);
+    bv[k] = (c < nc && k < d + 2) ? ca[c * sp + src] : 0.0;
+  }
+  __syncthreads();
+  const bool rbf = kernel_id == PLS_KERNEL_RBF;
+#pragma unroll 1
+  for (int r = 0; r < nrows; r += 4) {
+    double s[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int k = 0; k < NK; ++k) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) s[i] = fma(srow[(r + i) * NK + k], bv[k], s[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const double v = rbf ? gram_exp_fast(s[i], tbl) : s[i];
+      if (c < nc && r + i < nrows) out[(r0 + r + i) * ldo + c] = v;
+    }
+  }
+}
+
+cudaError_t launch_gram_fill(int kernel_id, const double* ra, int64_t nr, const double* ca, int64_t nc, int d, int sp, double* out,
+                             int64_t ldo, cudaStream_t stream) {
+  if (nr <= 0 || nc <= 0) return cudaSuccess;
+  dim3 grid((unsigned)((nc + GF_COLS - 1) / GF_COLS), (unsigned)((nr + GF_ROWS - 1) / GF_ROWS));
+  if ((nr + GF_ROWS - 1) / GF_ROWS > 65535) return cudaErrorInvalidConfiguration;
+  switch ((d + 2 + 3) / 4) {
+#define PLS_GF(q) \
+  case q: gram_fill_kernel<4 * q><<<grid, GF_COLS, 0, stream>>>(kernel_id, ra, nr, ca, nc, d, sp, out, ldo); break;
+    PLS_GF(1) PLS_GF(2) PLS_GF(3) PLS_GF(4) PLS_GF(5) PLS_GF(6) PLS_GF(7)
+#undef PLS_GF
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
 __global__ void gram_exp_kernel(const double* __restrict__ x, int64_t n, int fast, double* __restrict__ out) {
   __shared__ double tbl[64];
   if (threadIdx.x < 64) tbl[threadIdx.x] = kExp2Table[threadIdx.x];

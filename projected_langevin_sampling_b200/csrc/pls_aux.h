@@ -34,6 +34,8 @@ struct SmallGemmParams {
 
 cudaError_t launch_prepare_points(int kernel_id, const double* x, int64_t n, int d, int64_t ldx, const DimVec& inv_ls,
                                   const DimVec& centre, double c_extra, int sp, double* out, cudaStream_t stream);
+cudaError_t launch_gram_fill(int kernel_id, const double* ra, int64_t nr, const double* ca, int64_t nc, int d, int sp, double* out,
+                             int64_t ldo, cudaStream_t stream);
 cudaError_t launch_gram(int kernel_id, const double* ra, int64_t nr, const double* ca, int64_t nc, int d, int sp,
                         double* out, int64_t ldo, cudaStream_t stream);
 cudaError_t launch_philox_fill(uint64_t seed, uint64_t step, int64_t rows, int64_t j, int64_t joff, double* out,

@@ -52,9 +52,14 @@ class LangevinEngine:
                  inv_lambda: torch.Tensor, j: int, dc_budget_bytes: int = DEFAULT_DC_BUDGET,
                  gradient_reduce: Optional[Callable[[torch.Tensor], None]] = None,
                  weights_fn: Optional[Callable[[torch.Tensor, torch.Tensor], None]] = None, gram: Optional[torch.Tensor] = None,
-                 gaussian_normal_equations: bool = False):
+                 gaussian_normal_equations: bool = False, gram_staged: bool = False):
         self.ctx, self.kernel_id, self.d = ctx, kernel_id, d
         self.gram = gram  # ops.gram_cache(...) of (xa, za) or None: Gram values loaded instead of generated
+        # "staged" Gram: nothing N x M is kept -- every step re-forms k(X_c, Z) for the row chunk in flight into ONE chunk-sized
+        # buffer (pls_gram_fill_f64, ~1 % of the step) which that chunk's forward and backward launches then stream, instead of
+        # each of their J/256 column tiles regenerating it
+        self.kstage: Optional[torch.Tensor] = None
+        self._gram_staged = gram_staged and gram is None
         self.gaussian_normal_equations = gaussian_normal_equations  # opt-in, see _normal_equations()
         self._neq = None  # (key, A' in Gram-cache layout, b', y^T y / (2 s))
         self.xa, self.za, self.vt, self.inv_lambda = xa, za, vt, inv_lambda
@@ -69,6 +74,9 @@ class LangevinEngine:
         self.w = torch.zeros((self.m, self.ldj), dtype=torch.float64, device=dev)
         self.gm = torch.zeros((self.m, self.ldj), dtype=torch.float64, device=dev)
         self.dc = torch.zeros((self.chunk_rows, self.ldj), dtype=torch.float64, device=dev)
+        if self._gram_staged and self.n > 0:
+            self.kstage = torch.zeros((int(ctx.lib.pls_gram_cache_rows(self.chunk_rows)), int(ctx.lib.pls_gram_cache_ld(self.m))),
+                                      dtype=torch.float64, device=dev)
         self.splits = ops.backward_splits(ctx, self.chunk_rows, self.m, j)
         self.gp = torch.zeros((self.splits, self.m, self.ldj), dtype=torch.float64, device=dev)
         self.cost_partial: Optional[torch.Tensor] = None  # (row tiles, ldj), allocated by the first gradient(with_cost=True)
@@ -100,16 +108,20 @@ class LangevinEngine:
         t0 = 0
         for ci, (r0, r1) in enumerate(self.chunks):
             dc = self.dc[: r1 - r0]
+            if self.kstage is not None:
+                gram = ops.gram_fill(self.ctx, self.kernel_id, self.xa[r0:r1], self.za, self.d, self.kstage)
+            else:
+                gram = self._gram(r0)
             if with_cost:
                 t1 = t0 + (r1 - r0 + self.tile_rows - 1) // self.tile_rows
                 ops.forward_step(self.ctx, self.kernel_id, self.xa[r0:r1], self.za, self.d, self.w, self.j, cost, y[r0:r1], dc,
-                                 self.cost_partial[t0:t1], gram=self._gram(r0))
+                                 self.cost_partial[t0:t1], gram=gram)
                 t0 = t1
             else:
                 ops.forward(self.ctx, self.kernel_id, self.xa[r0:r1], self.za, self.d, self.w, self.j, nat.EPI_COST_DERIVATIVE,
-                            dc, cost=cost, y=y[r0:r1], gram=self._gram(r0))
+                            dc, cost=cost, y=y[r0:r1], gram=gram)
             ops.backward(self.ctx, self.kernel_id, self.za, self.xa[r0:r1], self.d, dc, self.j, self.gp, self.splits,
-                         accumulate=ci > 0, gram=self._gram(r0))
+                         accumulate=ci > 0, gram=gram)
         ops.reduce_splits(self.ctx, self.gp, self.j, self.gm)
         if self.gradient_reduce is not None:
             self.gradient_reduce(self.gm)

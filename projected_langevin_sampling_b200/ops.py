@@ -92,6 +92,16 @@ def gram_cache(ctx: nat.Context, kernel_id: int, rows_aug: torch.Tensor, cols_au
     return k
 
 
+def gram_fill(ctx: nat.Context, kernel_id: int, rows_aug: torch.Tensor, cols_aug: torch.Tensor, d: int, out: torch.Tensor) -> torch.Tensor:
+    """Rows [0, len(rows_aug)) of `out` (a gram_cache-shaped buffer) = k(rows, cols) at stream speed (pls_gram_fill_f64): the
+    per-chunk staging buffer of the engine's "staged" Gram mode."""
+    if rows_aug.shape[0] and cols_aug.shape[0]:
+        ctx.check(ctx.lib.pls_gram_fill_f64(ctx.handle, kernel_id, rows_aug.data_ptr(), rows_aug.shape[0], cols_aug.data_ptr(),
+                                            cols_aug.shape[0], d, out.data_ptr(), _ld(out), ctx.stream()))
+        ctx.launches += 1
+    return out
+
+
 def forward(ctx: nat.Context, kernel_id: int, xa: torch.Tensor, za: torch.Tensor, d: int, w: torch.Tensor, j: int,
             epilogue: int, out: torch.Tensor, cost: Optional[nat.PlsCost] = None, y: Optional[torch.Tensor] = None,
             gram: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -35,7 +35,8 @@ class OrthonormalBasis(PLSBasis):
                           step in M x M algebra (2 M^2 J flops instead of 4 N M J); see LangevinEngine._normal_equations
       gram_cache          False (default: Gram tiles regenerated inside the kernels, nothing N x M in memory) / True / "auto":
                           keep k(X, Z) resident in HBM, as the reference does (orthonormal.py:36-41), and stream it;
-                          "auto" does so when it fits comfortably (engine.want_gram_cache)
+                          "auto" does so when it fits comfortably (engine.want_gram_cache); "staged": re-form k(X_c, Z) every
+                          step for the row chunk in flight into one chunk-sized buffer shared by that chunk's launches
     """
 
     def __init__(self, kernel, x_induce: torch.Tensor, x_train: torch.Tensor, eigenvalue_threshold: float = 0.0,
@@ -103,12 +104,13 @@ class OrthonormalBasis(PLSBasis):
         eng = self._engines.get(number_of_particles)
         if eng is None:
             self._engines.clear()  # one set of workspaces at a time
-            if self._gram is None and want_gram_cache(self._gram_cache_mode, self.ctx, self._xa.shape[0], self._za.shape[0], self._xa.device):
+            if self._gram is None and self._gram_cache_mode != "staged" and want_gram_cache(self._gram_cache_mode, self.ctx, self._xa.shape[0], self._za.shape[0], self._xa.device):
                 self._gram = ops.gram_cache(self.ctx, self._spec.kernel_id, self._xa, self._za, self._d)  # k(X, Z), once
             eng = LangevinEngine(self.ctx, self._spec.kernel_id, self._d, self._xa, self._za, self.scaled_eigenvectors,
                                  self._inv_lambda, number_of_particles, dc_budget_bytes=self._dc_budget,
                                  gradient_reduce=self._gradient_reduce, gram=self._gram,
-                                 gaussian_normal_equations=self._gaussian_normal_equations)
+                                 gaussian_normal_equations=self._gaussian_normal_equations,
+                                 gram_staged=self._gram_cache_mode == "staged")
             self._engines[number_of_particles] = eng
         return eng
 

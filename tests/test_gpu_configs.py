@@ -4,7 +4,7 @@ C2 (N=10k, M=64, J=1024, Bernoulli) is checked in full against the oracle, inclu
 J=4096, Poisson f^2) and C4 (N=1M, D=8, M=1024, J=4096, Gaussian) are checked at FULL N and M on a slice of the particles
 (every term of the step is column-wise, orthonormal.py:151-158, so a slice of columns is the same computation) with the
 oracle's dense algebra evaluated in row chunks, plus size-independent properties on the full particle set.  Every config runs
-with the Gram generated inside the kernels and with the Gram cached in HBM (OrthonormalBasis(gram_cache=...)).
+with the Gram generated inside the kernels, cached in HBM, and staged chunk by chunk (OrthonormalBasis(gram_cache=...)).
 """
 import math
 
@@ -57,7 +57,7 @@ def _curve_inputs(n, kind, seed=0):
     return x, y, g
 
 
-@pytest.mark.parametrize("gram_cache", [False, True], ids=["generated", "cached"])
+@pytest.mark.parametrize("gram_cache", [False, True, "staged"], ids=["generated", "cached", "staged"])
 def test_config2_bernoulli_full(b200, gram_cache):
     """C2: N=10 000, D=1, M=64, J=1024, BernoulliCost + Sigmoid.  The selector is compared for the first 24 pivots: a 1-D RBF
     Gram with lengthscale 0.5 on [-3, 3] has numerical rank ~30, beyond which every conditional variance is round-off of the
@@ -103,7 +103,7 @@ def _chunked_oracle_update(kernel, x, y, z, vt, lam, p, eta, xi, dcost, chunk=50
     return -eta * (vt.T @ g) - eta * (p / lam[:, None]) + math.sqrt(2 * eta) * xi, g
 
 
-@pytest.mark.parametrize("gram_cache", [False, True], ids=["generated", "cached"])
+@pytest.mark.parametrize("gram_cache", [False, True, "staged"], ids=["generated", "cached", "staged"])
 def test_config3_poisson_full_rows(b200, gram_cache):
     """C3: N=100 000, D=1, M=256, PoissonCost + Square: a 192-particle slice at full N and M against the oracle, and the
     full J=4096 step's slice against the slice's own step (column independence)."""
@@ -136,7 +136,7 @@ def test_config3_poisson_full_rows(b200, gram_cache):
     assert rel_err(got_full[:, :j_slice], want) < TOL
 
 
-@pytest.mark.parametrize("gram_cache", [False, True], ids=["generated", "cached"])
+@pytest.mark.parametrize("gram_cache", [False, True, "staged"], ids=["generated", "cached", "staged"])
 def test_config4_gaussian_full_rows(b200, gram_cache):
     """C4: N=1 000 000, D=8 ARD, M=1024, GaussianCost: a 64-particle slice at full N and M against the oracle's dense algebra
     (row-chunked on the CPU), then properties of the full J=4096 step: its slice equals the slice's own step, the Philox
@@ -188,7 +188,7 @@ def test_config4_gaussian_full_rows(b200, gram_cache):
     assert np.isfinite(e_plain)
 
 
-@pytest.mark.parametrize("gram_cache", [False, True], ids=["generated", "cached"])
+@pytest.mark.parametrize("gram_cache", [False, True, "staged"], ids=["generated", "cached", "staged"])
 def test_gaussian_normal_equations_shortcut(b200, gram_cache):
     """Opt-in Gaussian / identity shortcut (LangevinEngine._normal_equations: A' = k(Z,X)k(X,Z)/s and b' = k(Z,X)y/s formed once,
     every step in M x M algebra): update and energy against the oracle, then 25 in-place steps and the fused training epoch

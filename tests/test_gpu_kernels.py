@@ -321,3 +321,27 @@ def test_generated_operand_gemm_random_shapes(ctx, n, m, d, j, ld):
         out = torch.empty(m, ld, dtype=torch.float64).cuda()
         ops.reduce_splits(ctx, gp, j, out)
         assert (out[:, :j] - want_g).abs().max().item() < 1e-11 * max(1.0, want_g.abs().max().item()) and (gp[:, :, j:] == -2.0).all()
+
+
+@pytest.mark.parametrize("n,m,d", [(1, 1, 1), (37, 129, 3), (1000, 300, 8), (4100, 64, 16), (513, 1000, 26)])
+def test_gram_fill_matches_gram(ctx, n, m, d):
+    """pls_gram_fill_f64 (the stream-speed fill of the cached / staged Gram buffers, table exp) against pls_gram_f64 (library
+    exp): a few ulps apart, nothing written outside rows [0, n) x columns [0, m)."""
+    from projected_langevin_sampling_b200 import _native as nat, ops
+
+    g = torch.Generator().manual_seed(n + m + d)
+    x = torch.randn(n, d, generator=g, dtype=torch.float64).cuda()
+    z = torch.randn(m, d, generator=g, dtype=torch.float64).cuda()
+    inv_ls = [1.0 / (1.0 + d ** 0.5 + 0.1 * k) for k in range(d)]
+    centre = z.mean(0).tolist()
+    for kid in (nat.KERNEL_RBF, nat.KERNEL_LINEAR):
+        xa = ops.prepare_points(ctx, kid, x, inv_ls, centre if kid == nat.KERNEL_RBF else [0.0] * d, 0.0)
+        za = ops.prepare_points(ctx, kid, z, inv_ls, centre if kid == nat.KERNEL_RBF else [0.0] * d, float(np.log(1.7)))
+        want = ops.gram(ctx, kid, xa, za, d)
+        ld = int(ctx.lib.pls_gram_cache_ld(m))
+        buf = torch.full((int(ctx.lib.pls_gram_cache_rows(n)) + 5, ld), -7.0, dtype=torch.float64).cuda()
+        ops.gram_fill(ctx, kid, xa, za, d, buf)
+        got = buf[:n, :m]
+        tol = 8 * np.finfo(np.float64).eps
+        assert ((got - want).abs() <= tol * want.abs().clamp_min(1e-300) + (1e-15 if kid == nat.KERNEL_LINEAR else 0.0)).all()
+        assert (buf[n:] == -7.0).all() and (buf[:, m:] == -7.0).all()
