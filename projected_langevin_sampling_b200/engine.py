@@ -32,15 +32,28 @@ ROW_ALIGN = 128
 DEFAULT_GRAM_CACHE_BYTES = 24 << 30
 
 
+def gram_mode(mode: Union[bool, str, None]) -> Union[bool, str]:
+    """Normalised Gram mode: False (generated, the default), True (cached), "auto" or "staged"; the environment variable
+    PLS_B200_GRAM_CACHE (off / on / auto / staged) overrides the argument."""
+    mode = os.environ.get("PLS_B200_GRAM_CACHE", mode if mode is not None else False)
+    if mode in (True, "on", "1", "true", "cached"):
+        return True
+    if mode in (False, "off", "0", "false", "generated"):
+        return False
+    if mode in ("auto", "staged"):
+        return mode
+    raise ValueError(f"unknown Gram mode {mode!r} (False / True / 'auto' / 'staged')")
+
+
 def want_gram_cache(mode: Union[bool, str, None], ctx: nat.Context, n: int, m: int, device: torch.device) -> bool:
     """Policy for keeping k(X, Z) resident.  mode: False / "off" (the default: Gram tiles are regenerated inside the kernels and
     nothing N x M is ever in memory, as BASELINE.json's north_star specifies), True / "on", or "auto": cache when it takes at
     most PLS_B200_GRAM_CACHE_BYTES (24 GiB) and a third of the free device memory.  The environment variable
     PLS_B200_GRAM_CACHE overrides the argument."""
-    mode = os.environ.get("PLS_B200_GRAM_CACHE", mode if mode is not None else False)
-    if mode in (True, "on", "1", "true"):
-        return True
-    if mode in (False, "off", "0", "false"):
+    mode = gram_mode(mode)
+    if mode is True or mode is False:
+        return mode
+    if mode == "staged":
         return False
     nbytes = int(ctx.lib.pls_gram_cache_rows(n)) * int(ctx.lib.pls_gram_cache_ld(m)) * 8
     free, _ = torch.cuda.mem_get_info(device)

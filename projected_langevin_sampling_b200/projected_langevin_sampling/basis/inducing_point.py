@@ -17,7 +17,7 @@ import torch
 
 from ... import _native as nat
 from ... import ops
-from ...engine import DEFAULT_DC_BUDGET, LangevinEngine, want_gram_cache
+from ...engine import DEFAULT_DC_BUDGET, LangevinEngine, gram_mode, want_gram_cache
 from ...kernels import dense_gram, kernel_spec
 from ...samplers import langevin_noise, sample_multivariate_normal
 from .base import PLSBasis
@@ -79,12 +79,12 @@ class InducingPointBasis(PLSBasis):
             def weights(particles: torch.Tensor, w: torch.Tensor) -> None:
                 w[:, : particles.shape[1]].copy_(self._solve(particles))  # W = k(Z, Z)^{-1} P
 
-            if self._gram is None and self._gram_cache_mode != "staged" and want_gram_cache(self._gram_cache_mode, self.ctx, self._xa.shape[0], self._za.shape[0], self._xa.device):
+            if self._gram is None and want_gram_cache(self._gram_cache_mode, self.ctx, self._xa.shape[0], self._za.shape[0], self._xa.device):
                 self._gram = ops.gram_cache(self.ctx, self._spec.kernel_id, self._xa, self._za, self._d)
             eye = torch.empty((self.approximation_dimension, 0), dtype=torch.float64, device=self.x_induce.device)
             eng = LangevinEngine(self.ctx, self._spec.kernel_id, self._d, self._xa, self._za, eye, self._m_over, number_of_particles,
                                  dc_budget_bytes=self._dc_budget, gradient_reduce=self._gradient_reduce, weights_fn=weights,
-                                 gram=self._gram, gram_staged=self._gram_cache_mode == "staged")
+                                 gram=self._gram, gram_staged=gram_mode(self._gram_cache_mode) == "staged")
             self._engines[number_of_particles] = eng
         return eng
 

@@ -13,7 +13,7 @@ import torch
 
 from ... import _native as nat
 from ... import ops
-from ...engine import DEFAULT_DC_BUDGET, LangevinEngine, want_gram_cache
+from ...engine import DEFAULT_DC_BUDGET, LangevinEngine, gram_mode, want_gram_cache
 from ...kernels import dense_gram, kernel_spec
 from ...samplers import langevin_noise, sample_multivariate_normal
 from .base import PLSBasis
@@ -104,13 +104,13 @@ class OrthonormalBasis(PLSBasis):
         eng = self._engines.get(number_of_particles)
         if eng is None:
             self._engines.clear()  # one set of workspaces at a time
-            if self._gram is None and self._gram_cache_mode != "staged" and want_gram_cache(self._gram_cache_mode, self.ctx, self._xa.shape[0], self._za.shape[0], self._xa.device):
+            if self._gram is None and want_gram_cache(self._gram_cache_mode, self.ctx, self._xa.shape[0], self._za.shape[0], self._xa.device):
                 self._gram = ops.gram_cache(self.ctx, self._spec.kernel_id, self._xa, self._za, self._d)  # k(X, Z), once
             eng = LangevinEngine(self.ctx, self._spec.kernel_id, self._d, self._xa, self._za, self.scaled_eigenvectors,
                                  self._inv_lambda, number_of_particles, dc_budget_bytes=self._dc_budget,
                                  gradient_reduce=self._gradient_reduce, gram=self._gram,
                                  gaussian_normal_equations=self._gaussian_normal_equations,
-                                 gram_staged=self._gram_cache_mode == "staged")
+                                 gram_staged=gram_mode(self._gram_cache_mode) == "staged")
             self._engines[number_of_particles] = eng
         return eng
 
