@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- particle-updates/sec of the fused PLS Langevin step (BASELINE.json metric) on N B200s.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c4|c3|c2]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c4|c3|c2|c5] [--grid RxC] [--gram generated|staged|cached|auto]
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
 A "step" is one Langevin step over all J particles of the workload:
@@ -12,6 +12,10 @@ X, y, Z, V~, lambda; no per-step communication; Philox noise keyed on the global
 The JSON line carries: value (device-timed, inputs resident in HBM), e2e (through the reference-facing API with pinned
 HOST buffers, copies inside the timed region), roofline (FP64 tensor, live CUDA-event kernel timing), cpu_baseline
 (the oracle's reference-style torch-CPU step on the box's host cores, bounded sample), clocks, gpu_launches.
+Every timed number above is the DEFAULT path (Gram tiles regenerated inside the kernels, nothing N x M in memory, --gram generated).
+At N = 1 the line also carries informational measurements taken after and outside the timed region: library_bar (the
+reference's algebra on cuBLAS on this GPU), gram_cached / gram_staged (the same steps with the two opt-in Gram modes) and
+gaussian_normal_equations (the opt-in M x M re-association for the Gaussian cost).
 
 `--impl reference` times the reference's own CPU formulation of the path (the oracle port -- the reference itself needs
 gpytorch, which is not installed) on all host threads and prints the same line shape with "impl": "reference".
