@@ -212,3 +212,20 @@ def test_bench_reference_arm_prints_one_contract_line():
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     for key in ("metric", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "vs_baseline", "dtype", "data", "config"):
         assert key in d
+
+
+def test_gram_mode_argument_and_environment(monkeypatch):
+    """engine.gram_mode: the default is the generated Gram (nothing N x M in memory, BASELINE.json north_star); the other modes
+    are opt-in by argument or by PLS_B200_GRAM_CACHE, and anything else is an error."""
+    from projected_langevin_sampling_b200.engine import gram_mode
+
+    monkeypatch.delenv("PLS_B200_GRAM_CACHE", raising=False)
+    assert gram_mode(None) is False and gram_mode(False) is False and gram_mode("generated") is False
+    assert gram_mode(True) is True and gram_mode("cached") is True
+    assert gram_mode("auto") == "auto" and gram_mode("staged") == "staged"
+    with pytest.raises(ValueError):
+        gram_mode("sometimes")
+    monkeypatch.setenv("PLS_B200_GRAM_CACHE", "staged")
+    assert gram_mode(False) == "staged"
+    monkeypatch.setenv("PLS_B200_GRAM_CACHE", "off")
+    assert gram_mode(True) is False
