@@ -379,3 +379,31 @@ def test_ipb_predictive_noise_and_predict_reference_vectors():
     assert torch.allclose(got, noise_want, rtol=1e-3, atol=1e-2)
     pred = ipb().predict_untransformed_samples(P23.double(), xs.double(), noise_want.double())
     assert torch.allclose(pred.float(), torch.tensor([[-4.4373, -3.6672, 2.9305], [-7.8718, -6.6582, 8.8616]]), rtol=2e-3, atol=2e-3)
+
+
+def test_gaussian_normal_equations_identity_on_the_oracle():
+    """The algebra behind the opt-in Gaussian shortcut (LangevinEngine._normal_equations), checked on the CPU oracle alone: with the
+    Gaussian cost and the identity link the oracle's update and energy equal the M x M forms built from A' = k(Z,X) k(X,Z) / s,
+    b' = k(Z,X) y / s (orthonormal.py:98-108,151-158 re-associated with costs/gaussian.py:54-88)."""
+    g = torch.Generator().manual_seed(3)
+    n, d, m, j, s_obs, eta = 400, 3, 24, 17, 0.3, 1e-3
+    x = torch.randn(n, d, generator=g, dtype=torch.float64)
+    y = torch.sin(x.sum(1)) + 0.1 * torch.randn(n, generator=g, dtype=torch.float64)
+    z = x[:m].clone()
+    kernel = RBFScaleKernel(torch.tensor([1.2, 1.5, 1.8], dtype=torch.float64), 1.4)
+    basis = OrthonormalBasisOracle(kernel, z, x, eigenvalue_threshold=1e-9)
+    orc = PLSOracle(basis, Cost("gaussian", y, Link("identity"), observation_noise=s_obs))
+    m_k = basis.approximation_dimension
+    p = torch.randn(m_k, j, generator=g, dtype=torch.float64)
+    xi = torch.randn(m_k, j, generator=g, dtype=torch.float64)
+    k_xz = kernel(x, z)
+    vt, lam = basis.scaled_eigenvectors, basis.eigenvalues
+    a, b = k_xz.T @ k_xz / s_obs, k_xz.T @ y / s_obs
+    w = vt @ p
+    aw = a @ w
+    delta = -eta * (vt.T @ (aw - b[:, None])) - eta * p / lam[:, None] + np.sqrt(2 * eta) * xi
+    want = orc.calculate_particle_update(p, eta, noise=xi)
+    assert (delta - want).abs().max() <= 1e-11 * want.abs().max()
+    cost = 0.5 * (w * aw).sum(0) - b @ w + (y @ y) / (2 * s_obs)
+    energy = (cost + 0.5 * (p * p / lam[:, None]).sum(0)).mean().item()
+    assert abs(energy - orc.calculate_energy_potential(p)) <= 1e-11 * abs(energy)
