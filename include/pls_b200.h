@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define PLS_ABI_VERSION 1
+#define PLS_ABI_VERSION 2
 
 /* base kernel k(x, x') -- pls/kernel.py:21-29 `.base_kernel`; gpytorch ScaleKernel(RBFKernel(ard_num_dims=D)) at the
  * reference call sites pls/basis/orthonormal.py:36-41, src/inducing_point_selectors/conditional_variance.py:66-89;
@@ -236,31 +236,103 @@ int pls_lincomb3_f64(pls_ctx* ctx, int64_t rows, int64_t j, double a, const doub
  * hot kernel uses for the cost functors (csrc/pls_cost.cuh FlatMath).  Exposed so the tests can bound their error in ulps. */
 int pls_flat_math_f64(pls_ctx* ctx, int op, const double* a, const double* b, int64_t n, double* out, void* stream);
 
+/* ---- one call per Langevin step ---------------------------------------------------------------------------------
+ * PLS.calculate_particle_update (pls/projected_langevin_sampling.py:107-123 -> pls/basis/orthonormal.py:98-108,
+ * pls/costs/<cost>.py, orthonormal.py:128-159) as ONE call over caller-owned workspaces: W = V~ P, the row-chunk loop
+ * (forward with the cost derivative in its epilogue, backward), the split reduction and -- pls_step_f64 -- the update.
+ * pls_step_plan_f64 (host only) fixes the chunking of the training rows and the layout of the workspace:
+ *   dc_budget_bytes  bound on the only N-sized intermediate, the Dc chunk (<= 0: 8 GiB);
+ *   gram_mode        PLS_GRAM_GENERATED: Gram tiles regenerated inside the kernels, nothing N x M in memory (default path);
+ *                    PLS_GRAM_STAGED:    k(X_c, Z) of the chunk in flight re-formed every step into a chunk-sized region of the
+ *                                        workspace (pls_gram_fill_f64) and streamed by that chunk's two launches;
+ *                    PLS_GRAM_CACHED:    the caller keeps k(X, Z) (pls_gram_f64 layout of the pls_*_cached_f64 calls) and passes it;
+ *   with_cost        reserve room for the per-row-tile cost sums (needed when cost_sums / energy_out is requested).
+ * The workspace is plan->workspace_bytes bytes of device memory, 256-byte aligned; after pls_grad_f64 the gradient
+ * G' = k(Z,X) d_2 c(y, k(X,Z) V~ P) (M x J, leading dimension plan->ldj) sits at byte offset plan->off_gm and W at plan->off_w. */
+enum { PLS_GRAM_GENERATED = 0, PLS_GRAM_STAGED = 1, PLS_GRAM_CACHED = 2 };
+typedef struct pls_step_plan {
+  int64_t n, m, m_k, j, ldj;
+  int64_t chunk_rows;   /* training rows per forward/backward launch pair */
+  int64_t cost_tiles;   /* rows of the cost-partial region: sum over chunks of ceil(rows / tile_rows) */
+  int32_t n_chunks, splits, tile_rows, gram_mode, with_cost, reserved;
+  int64_t off_w, off_gm, off_dc, off_gp, off_cost_partial, off_kstage; /* byte offsets into the workspace */
+  int64_t workspace_bytes;
+} pls_step_plan;
+int pls_step_plan_f64(const pls_ctx* ctx, int64_t n, int64_t m, int64_t m_k, int64_t j, int64_t dc_budget_bytes, int gram_mode,
+                      int with_cost, pls_step_plan* plan);
+/* The gradient G' into the workspace (see above).  xa: n x SP, za: m x SP augmented points; vt: M x M_k (ldv) or NULL when `p`
+ * already holds W (M x J, ldp even, 16-byte aligned: the InducingPointBasis passes k(Z,Z)^{-1} P); p: M_k x J particles (ldp);
+ * gram/ldk: the resident Gram for PLS_GRAM_CACHED, else NULL/0; cost_sums (nullable): J doubles, sum_n c(y_n, F[n][j]) of the SAME
+ * forward pass (PLS.calculate_cost, pls/projected_langevin_sampling.py:75-88).  Row-sharded callers all-reduce the gradient (and
+ * cost_sums) over their row group and then call pls_project_update_f64. */
+int pls_grad_f64(pls_ctx* ctx, const pls_step_plan* plan, int kernel_id, int d, const double* xa, const double* za, const double* vt,
+                 int64_t ldv, const double* p, int64_t ldp, const pls_cost* cost, const double* y, const double* gram, int64_t ldk,
+                 void* workspace, double* cost_sums, void* stream);
+/* pls_grad_f64 followed by pls_project_update_f64 (same noise / in_place / out arguments).  energy_out (nullable): J doubles, the
+ * per-particle energy potential of the INPUT particles, cost + 1/2 sum_m P_mj^2 / lambda_m (orthonormal.py:110-126 before its mean),
+ * from the same forward pass -- what experiments/trainers.py:153-158 pays a second forward for. */
+int pls_step_f64(pls_ctx* ctx, const pls_step_plan* plan, int kernel_id, int d, const double* xa, const double* za, const double* vt,
+                 int64_t ldv, const double* inv_lambda, double* p, int64_t ldp, const pls_cost* cost, const double* y,
+                 const double* gram, int64_t ldk, double eta, int noise_mode, const double* xi, int64_t ldxi, uint64_t seed,
+                 uint64_t step, int64_t j_global_offset, int in_place, double* out, int64_t ldo, double* energy_out, void* workspace,
+                 void* stream);
+
+/* ---- per-role kernel timing ---------------------------------------------------------------------------------------
+ * Between pls_profile_begin and pls_profile_end every launch of the contraction kernel (through any entry point above) is
+ * bracketed by a CUDA-event pair on the launching stream.  pls_profile_end synchronises those events and returns
+ * out6 = {forward ms, forward launches, forward algorithmic flops (2 n m j each), backward ms, launches, flops}.
+ * bench.py's roofline figures come from this; it costs two event records per launch and is off by default. */
+int pls_profile_begin(pls_ctx* ctx);
+int pls_profile_end(pls_ctx* ctx, double* out6);
+
 /* ---- ConditionalVariance inducing-point selector ------------------------------------------------------------- */
 /* Greedy pivoted Cholesky (src/inducing_point_selectors/conditional_variance.py:27-120) on the ALREADY PERMUTED
  * points xp_aug (augmented layout, n rows; the numpy permutation of :60 stays on the host).
  *   kdiag: the value diag k(x, x) takes (outputscale for RBF -- exact, as gpytorch returns it), ignored for LINEAR
  *          where the diagonal is computed;
- *   ci: workspace (m-1) x n doubles; di: workspace n doubles; scratch: workspace pls_cv_scratch_doubles(n) doubles;
+ *   ci: workspace (m-1) x n doubles; di: workspace n doubles; scratch: workspace pls_cv_scratch_doubles(n, d, m) doubles;
  *   indices_out: m int64 in DEVICE memory, pre-filled by the caller with the sentinel n (as :63); receives positions in
  *          the permuted order, entries never reached keep the sentinel;
- *   n_selected_out (host int*): how many entries were filled.  Synchronises the stream before returning. */
-int64_t pls_cv_scratch_doubles(int64_t n);
+ *   n_selected_out (host int*): how many entries were filled.  Synchronises the stream before returning.
+ *
+ * Exact ties.  The reference takes "the last entry of np.argsort(d) that is not chosen yet" (:105-109).  numpy's default
+ * argsort is not stable, so when the largest conditional variance is attained by SEVERAL points (1-D inputs with a short
+ * lengthscale do this: every point far from all pivots keeps d = outputscale + jitter to the last bit) the reference's choice
+ * is whatever numpy's sort routine makes of that array.  The kernels count how often the maximum is attained:
+ *   PLS_CV_TIES_HOST          when it is attained more than once the selector pauses, copies d (n doubles) and the pivots
+ *                             chosen so far to the host and calls tie_fn, which returns the position of the next pivot
+ *                             (the Python layer passes exactly the reference's two lines); unambiguous pivots never
+ *                             leave the device;
+ *   PLS_CV_TIES_HIGHEST_INDEX the highest permuted index among the tied points (what a stable argsort gives); no host
+ *                             round trip at all; tie_fn is ignored.
+ * After the call the scratch header holds, as doubles / int64 bit patterns: [3] n_selected, [4] sum(d) after the last update,
+ * [8] the smallest relative gap (max - runner-up) / max seen at any pivot choice (0 if a tie occurred: how close the
+ * selection came to depending on round-off), [9] the number of pivots chosen among tied maxima. */
+#define PLS_CV_HEADER_DOUBLES 16
+enum { PLS_CV_TIES_HIGHEST_INDEX = 0, PLS_CV_TIES_HOST = 1 };
+typedef int64_t (*pls_cv_tie_fn)(void* user, const double* d_host, int64_t n, const int64_t* chosen, int n_chosen);
+int64_t pls_cv_scratch_doubles(int64_t n, int d, int m);
 int pls_cv_select_f64(pls_ctx* ctx, int kernel_id, const double* xp_aug, int64_t n, int d, double kdiag, int m,
-                      double jitter, double threshold, int has_threshold, double* ci, double* di, double* scratch,
-                      int64_t* indices_out, int* n_selected_out, void* stream);
+                      double jitter, double threshold, int has_threshold, int tie_mode, pls_cv_tie_fn tie_fn, void* tie_user,
+                      double* ci, double* di, double* scratch, int64_t* indices_out, int* n_selected_out, void* stream);
 
 /* ---- the selector with the points sharded by rows over several GPUs -------------------------------------------- */
 /* Rank r holds rows [n_offset, n_offset + n_local) of the permuted point set, its slice of C ((m-1) x n_local) and of d.
  * Per pivot every rank publishes ONE candidate record (pls_cv_candidate_doubles(d, m) doubles: value, global index,
- * local sum of d, the candidate's augmented point and its column of C); the HOST all-gathers the records of all ranks
- * (torch.distributed / NCCL, the only exchange: <= (m + SP + 4) doubles per rank and pivot) and every rank picks the same
- * pivot from them with the single-GPU rules (ties by GLOBAL index), so the selected indices equal pls_cv_select_f64's.
+ * local sum of d, multiplicity, runner-up, the candidate's augmented point and its column of C); the HOST all-gathers the
+ * records of all ranks (torch.distributed / NCCL, the only exchange: <= (m + SP + 8) doubles per rank and pivot) and every
+ * rank picks the same pivot from them with the single-GPU rules, so the selected indices equal pls_cv_select_f64's.
  *   pls_cv_shard_begin_f64 : d = diag + jitter; candidate for pivot 0
  *   [all-gather]  pls_cv_shard_pick_f64(slot = 0)
  *   for i in 0 .. m-2:  pls_cv_shard_update_f64(iter = i)  (rank-1 update with the published pivot; candidate for pivot i+1)
  *                       [all-gather]  pls_cv_shard_pick_f64(slot = i + 1)
  *   pls_cv_shard_finish    : synchronises, returns how many pivots were chosen
+ * Ties (tie_mode as above): with PLS_CV_TIES_HOST a pick that finds the maximum attained more than once (over all ranks)
+ * publishes nothing and sets the pause flag; later update / pick calls are no-ops until the host has decided.  The host
+ * reads pls_cv_shard_status (synchronises; status4 = {n_selected, stopped, tie pending, slot of the tie}), gathers the
+ * ranks' slices of d, decides, and pushes the pivot back on every rank with
+ *   pls_cv_shard_force_f64(slot, pivot)  [all-gather]  pls_cv_shard_pick_f64(slot, forced = 1)
+ * and resumes with pls_cv_shard_update_f64(iter = slot).
  * indices_out: m int64 GLOBAL positions in the permuted order, pre-filled with the sentinel n_total by the caller.
  * scratch: pls_cv_shard_scratch_doubles(n_local, d, m) doubles, private to the rank. */
 int64_t pls_cv_shard_scratch_doubles(int64_t n_local, int d, int m);
@@ -268,11 +340,14 @@ int64_t pls_cv_candidate_doubles(int d, int m);
 int pls_cv_shard_begin_f64(pls_ctx* ctx, int kernel_id, const double* xa_local, int64_t n_local, int64_t n_offset, int d,
                            double kdiag, int m, double jitter, double* di, double* scratch, double* candidate, void* stream);
 int pls_cv_shard_pick_f64(pls_ctx* ctx, const double* candidates, int world, int slot, int d, int m, double threshold,
-                          int has_threshold, int64_t n_local, int64_t n_offset, double* scratch, int64_t* indices_out,
-                          void* stream);
+                          int has_threshold, int tie_mode, int forced, int64_t n_local, int64_t n_offset, double* scratch,
+                          int64_t* indices_out, void* stream);
 int pls_cv_shard_update_f64(pls_ctx* ctx, int kernel_id, const double* xa_local, int64_t n_local, int64_t n_offset, int d,
                             int iter, int m, double jitter, double* ci, double* di, double* scratch, double* candidate,
                             void* stream);
+int pls_cv_shard_force_f64(pls_ctx* ctx, const double* xa_local, int64_t n_local, int64_t n_offset, int d, int m, int slot,
+                           int64_t pivot, const double* ci, const double* di, double* scratch, double* candidate, void* stream);
+int pls_cv_shard_status(pls_ctx* ctx, const double* scratch, int64_t* status4, void* stream);
 int pls_cv_shard_finish(pls_ctx* ctx, const double* scratch, int* n_selected_out, void* stream);
 
 #ifdef __cplusplus

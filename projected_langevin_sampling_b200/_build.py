@@ -46,7 +46,7 @@ def _source_hash() -> str:
 
 
 def _units():
-    units = [("pls_api.cu", [], "pls_api.o"), ("pls_aux.cu", [], "pls_aux.o"), ("pls_selector.cu", [], "pls_selector.o"),
+    units = [("pls_api.cu", [], "pls_api.o"), ("pls_aux.cu", [], "pls_aux.o"), ("pls_selector.cu", [], "pls_selector.o"), ("pls_step.cu", [], "pls_step.o"),
              ("pls_gen_gemm.cu", [], "pls_gen_gemm.o")]
     for k in range(1, MAX_NKD + 1):
         for role in range(5):  # forward epilogues PLS_EPI_* (0..3), backward (4)

@@ -21,7 +21,9 @@ COST_GAUSSIAN, COST_BERNOULLI, COST_POISSON, COST_MULTIMODAL, COST_STUDENT_T = r
 LINK_IDENTITY, LINK_SIGMOID, LINK_PROBIT, LINK_SQUARE = range(4)
 EPI_PREDICTION, EPI_COST_DERIVATIVE, EPI_COST, EPI_COST_DERIVATIVE_AND_COST = range(4)
 NOISE_NONE, NOISE_GIVEN, NOISE_PHILOX = range(3)
-ABI_VERSION = 1
+CV_TIES_HIGHEST_INDEX, CV_TIES_HOST = 0, 1
+CV_HEADER_DOUBLES = 16
+ABI_VERSION = 2
 COST_VALUE_TILE_ROWS = 128  # rows per partial sum of pls_cost_value_f64 (dense F)
 
 
@@ -46,12 +48,25 @@ class PlsCost(C.Structure):
     ]
 
 
+class StepPlan(C.Structure):
+    """struct pls_step_plan"""
+
+    _fields_ = [(k, C.c_int64) for k in ("n", "m", "m_k", "j", "ldj", "chunk_rows", "cost_tiles")] + \
+               [(k, C.c_int32) for k in ("n_chunks", "splits", "tile_rows", "gram_mode", "with_cost", "reserved")] + \
+               [(k, C.c_int64) for k in ("off_w", "off_gm", "off_dc", "off_gp", "off_cost_partial", "off_kstage", "workspace_bytes")]
+
+
+GRAM_GENERATED, GRAM_STAGED, GRAM_CACHED = range(3)
+
+
 class NativeLibraryError(RuntimeError):
     pass
 
 
 _i64, _int, _dbl, _vp, _u64 = C.c_int64, C.c_int, C.c_double, C.c_void_p, C.c_uint64
 _costp = C.POINTER(PlsCost)
+# int64_t (*pls_cv_tie_fn)(void* user, const double* d_host, int64_t n, const int64_t* chosen, int n_chosen)
+CV_TIE_FN = C.CFUNCTYPE(C.c_int64, C.c_void_p, C.POINTER(C.c_double), C.c_int64, C.POINTER(C.c_int64), C.c_int)
 
 # name -> (restype, argtypes); kept in the order of include/pls_b200.h
 SIGNATURES = {
@@ -90,14 +105,23 @@ SIGNATURES = {
     "pls_gram_exp_f64": (_int, [_vp, _vp, _i64, _int, _vp, _vp]),
     "pls_lincomb3_f64": (_int, [_vp, _i64, _i64, _dbl, _vp, _i64, _dbl, _vp, _i64, _dbl, _vp, _i64, _vp, _i64, _vp, _i64, _vp]),
     "pls_flat_math_f64": (_int, [_vp, _int, _vp, _vp, _i64, _vp, _vp]),
-    "pls_cv_scratch_doubles": (_i64, [_i64]),
+    "pls_step_plan_f64": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _int, _int, C.POINTER(StepPlan)]),
+    "pls_grad_f64": (_int, [_vp, C.POINTER(StepPlan), _int, _int, _vp, _vp, _vp, _i64, _vp, _i64, _costp, _vp, _vp, _i64, _vp, _vp, _vp]),
+    "pls_step_f64": (_int, [_vp, C.POINTER(StepPlan), _int, _int, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _costp, _vp, _vp, _i64, _dbl, _int,
+                            _vp, _i64, _u64, _u64, _i64, _int, _vp, _i64, _vp, _vp, _vp]),
+    "pls_profile_begin": (_int, [_vp]),
+    "pls_profile_end": (_int, [_vp, C.POINTER(_dbl)]),
+    "pls_cv_scratch_doubles": (_i64, [_i64, _int, _int]),
     "pls_cv_shard_scratch_doubles": (_i64, [_i64, _int, _int]),
     "pls_cv_candidate_doubles": (_i64, [_int, _int]),
     "pls_cv_shard_begin_f64": (_int, [_vp, _int, _vp, _i64, _i64, _int, _dbl, _int, _dbl, _vp, _vp, _vp, _vp]),
-    "pls_cv_shard_pick_f64": (_int, [_vp, _vp, _int, _int, _int, _int, _dbl, _int, _i64, _i64, _vp, _vp, _vp]),
+    "pls_cv_shard_pick_f64": (_int, [_vp, _vp, _int, _int, _int, _int, _dbl, _int, _int, _int, _i64, _i64, _vp, _vp, _vp]),
     "pls_cv_shard_update_f64": (_int, [_vp, _int, _vp, _i64, _i64, _int, _int, _int, _dbl, _vp, _vp, _vp, _vp, _vp]),
+    "pls_cv_shard_force_f64": (_int, [_vp, _vp, _i64, _i64, _int, _int, _int, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "pls_cv_shard_status": (_int, [_vp, _vp, C.POINTER(_i64), _vp]),
     "pls_cv_shard_finish": (_int, [_vp, _vp, C.POINTER(_int), _vp]),
-    "pls_cv_select_f64": (_int, [_vp, _int, _vp, _i64, _int, _dbl, _int, _dbl, _dbl, _int, _vp, _vp, _vp, _vp, C.POINTER(_int), _vp]),
+    "pls_cv_select_f64": (_int, [_vp, _int, _vp, _i64, _int, _dbl, _int, _dbl, _dbl, _int, _int, CV_TIE_FN, _vp, _vp, _vp, _vp, _vp,
+                                 C.POINTER(_int), _vp]),
 }
 
 _lib: Optional[C.CDLL] = None

@@ -37,6 +37,31 @@ int check_cost(pls_ctx* ctx, const pls_cost* c) {
   return 0;
 }
 
+// CUDA-event pair around one launch of the hot kernel while pls_profile_begin is in effect
+struct ProfileScope {
+  pls_ctx* ctx;
+  cudaStream_t stream;
+  pls_ctx::ProfileRecord rec{};
+  bool on = false;
+  ProfileScope(pls_ctx* c, int role, double flops, cudaStream_t s) : ctx(c), stream(s) {
+    if (!c || !c->profiling) return;
+    rec.role = role;
+    rec.flops = flops;
+    if (cudaEventCreate(&rec.e0) != cudaSuccess) return;
+    if (cudaEventCreate(&rec.e1) != cudaSuccess) {
+      cudaEventDestroy(rec.e0);
+      return;
+    }
+    cudaEventRecord(rec.e0, s);
+    on = true;
+  }
+  ~ProfileScope() {
+    if (!on) return;
+    cudaEventRecord(rec.e1, stream);
+    ctx->profile.push_back(rec);
+  }
+};
+
 int check_kernel(pls_ctx* ctx, int kernel_id, int d) {
   if (kernel_id != PLS_KERNEL_RBF && kernel_id != PLS_KERNEL_LINEAR) return fail(ctx, "unknown kernel_id %d", kernel_id);
   if (d < 1 || d > pls::MAX_D) return fail(ctx, "input dimension d=%d outside [1, %d]", d, pls::MAX_D);
@@ -72,11 +97,54 @@ int pls_ctx_create(int device, pls_ctx** out) {
   return 0;
 }
 
-void pls_ctx_destroy(pls_ctx* ctx) { delete ctx; }
+void pls_ctx_destroy(pls_ctx* ctx) {
+  if (ctx)
+    for (auto& r : ctx->profile) {
+      cudaEventDestroy(r.e0);
+      cudaEventDestroy(r.e1);
+    }
+  delete ctx;
+}
 
 const char* pls_last_error(const pls_ctx* ctx) { return ctx ? ctx->error.c_str() : g_create_error.c_str(); }
 
 int pls_sm_count(const pls_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
+
+static void drop_profile(pls_ctx* ctx) {
+  for (auto& r : ctx->profile) {
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  ctx->profile.clear();
+}
+
+int pls_profile_begin(pls_ctx* ctx) {
+  if (!ctx) return 1;
+  drop_profile(ctx);
+  ctx->profiling = true;
+  return 0;
+}
+
+int pls_profile_end(pls_ctx* ctx, double* out6) {
+  if (!ctx) return 1;
+  ctx->profiling = false;
+  double acc[6] = {0, 0, 0, 0, 0, 0};
+  cudaError_t err = cudaSuccess;
+  for (auto& r : ctx->profile) {
+    float ms = 0.f;
+    cudaError_t e = cudaEventSynchronize(r.e1);
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, r.e0, r.e1);
+    if (e != cudaSuccess) err = e;
+    double* a = acc + (r.role == 0 ? 0 : 3);
+    a[0] += ms;
+    a[1] += 1.0;
+    a[2] += r.flops;
+  }
+  drop_profile(ctx);
+  if (out6)
+    for (int i = 0; i < 6; ++i) out6[i] = acc[i];
+  return check_cuda(ctx, err, "pls_profile_end");
+}
 
 int pls_point_stride(int d) {
   if (d < 1 || d > pls::MAX_D) return -1;
@@ -200,6 +268,7 @@ static int forward_common(pls_ctx* ctx, const char* who, int kernel_id, const do
   p.sp = pls::point_stride(d); p.d = d; p.kernel_id = kernel_id; p.epilogue = epilogue; p.splits = 1; p.accumulate = 0;
   p.rt = pls::choose_tile_rt(ctx, j);
   p.out = out; p.ldo = ldo; p.out2 = out2; p.ldo2 = ldo2; p.y = y;
+  ProfileScope scope(ctx, 0, 2.0 * (double)n * (double)m * (double)j, (cudaStream_t)stream);
   return check_cuda(ctx, pls::launch_gen_gemm_forward(ctx, p, (cudaStream_t)stream), who);
 }
 
@@ -254,6 +323,7 @@ static int backward_common(pls_ctx* ctx, const char* who, int kernel_id, const d
   p.accumulate = accumulate; p.out = gp; p.ldo = ldg; p.y = nullptr; p.rt = pls::choose_tile_rt(ctx, j);
   if (n == 0 && !accumulate && m > 0)  // an empty row shard contributes a zero gradient (no kernel is launched)
     return check_cuda(ctx, cudaMemsetAsync(gp, 0, sizeof(double) * (size_t)splits * (size_t)m * (size_t)ldg, (cudaStream_t)stream), who);
+  ProfileScope scope(ctx, 1, 2.0 * (double)n * (double)m * (double)j, (cudaStream_t)stream);
   return check_cuda(ctx, pls::launch_gen_gemm_backward(ctx, p, (cudaStream_t)stream), who);
 }
 
@@ -363,20 +433,25 @@ int pls_flat_math_f64(pls_ctx* ctx, int op, const double* a, const double* b, in
   return check_cuda(ctx, pls::launch_flat_math(op, a, b ? b : a, n, out, (cudaStream_t)stream), "pls_flat_math_f64");
 }
 
-int64_t pls_cv_scratch_doubles(int64_t n) { return n < 0 ? 0 : pls::cv_scratch_doubles(n); }
+int64_t pls_cv_scratch_doubles(int64_t n, int d, int m) {
+  return (n < 0 || d < 1 || d > pls::MAX_D || m < 2) ? 0 : pls::cv_scratch_doubles(n, d, m);
+}
 
 int pls_cv_select_f64(pls_ctx* ctx, int kernel_id, const double* xp_aug, int64_t n, int d, double kdiag, int m,
-                      double jitter, double threshold, int has_threshold, double* ci, double* di, double* scratch,
-                      int64_t* indices_out, int* n_selected_out, void* stream) {
+                      double jitter, double threshold, int has_threshold, int tie_mode, pls_cv_tie_fn tie_fn, void* tie_user,
+                      double* ci, double* di, double* scratch, int64_t* indices_out, int* n_selected_out, void* stream) {
   if (!ctx) return 1;
   if (check_kernel(ctx, kernel_id, d)) return 1;
   if (!xp_aug || !ci || !di || !scratch || !indices_out || !n_selected_out) return fail(ctx, "pls_cv_select_f64: NULL argument");
   if (m < 2) return fail(ctx, "pls_cv_select_f64: Must have at least 2 inducing points");
   if (n < m) return fail(ctx, "pls_cv_select_f64: m=%d exceeds the number of points n=%lld", m, (long long)n);
-  return check_cuda(ctx,
-                    pls::run_cv_select(ctx, kernel_id, xp_aug, n, d, kdiag, m, jitter, threshold, has_threshold, ci, di,
-                                       scratch, indices_out, n_selected_out, (cudaStream_t)stream),
-                    "pls_cv_select_f64");
+  if (tie_mode != PLS_CV_TIES_HIGHEST_INDEX && tie_mode != PLS_CV_TIES_HOST) return fail(ctx, "pls_cv_select_f64: unknown tie_mode %d", tie_mode);
+  if (tie_mode == PLS_CV_TIES_HOST && !tie_fn) return fail(ctx, "pls_cv_select_f64: PLS_CV_TIES_HOST needs a tie_fn");
+  const cudaError_t e = pls::run_cv_select(ctx, kernel_id, xp_aug, n, d, kdiag, m, jitter, threshold, has_threshold, tie_mode, tie_fn,
+                                           tie_user, ci, di, scratch, indices_out, n_selected_out, (cudaStream_t)stream);
+  if (e == cudaErrorInvalidValue && tie_mode == PLS_CV_TIES_HOST)
+    return fail(ctx, "pls_cv_select_f64: the tie callback returned an index that is out of range or already chosen");
+  return check_cuda(ctx, e, "pls_cv_select_f64");
 }
 
 int64_t pls_cv_shard_scratch_doubles(int64_t n_local, int d, int m) {
@@ -396,12 +471,14 @@ int pls_cv_shard_begin_f64(pls_ctx* ctx, int kernel_id, const double* xa_local, 
 }
 
 int pls_cv_shard_pick_f64(pls_ctx* ctx, const double* candidates, int world, int slot, int d, int m, double threshold,
-                          int has_threshold, int64_t n_local, int64_t n_offset, double* scratch, int64_t* indices_out, void* stream) {
+                          int has_threshold, int tie_mode, int forced, int64_t n_local, int64_t n_offset, double* scratch,
+                          int64_t* indices_out, void* stream) {
   if (!ctx) return 1;
-  if (!candidates || world < 1 || slot < 0 || slot >= m || d < 1 || d > pls::MAX_D || !scratch || !indices_out)
+  if (!candidates || world < 1 || slot < 0 || slot >= m || d < 1 || d > pls::MAX_D || !scratch || !indices_out ||
+      (tie_mode != PLS_CV_TIES_HIGHEST_INDEX && tie_mode != PLS_CV_TIES_HOST))
     return fail(ctx, "pls_cv_shard_pick_f64: bad arguments");
-  return check_cuda(ctx, pls::cv_shard_pick(candidates, world, slot, d, m, threshold, has_threshold, n_local, n_offset, scratch,
-                                            indices_out, (cudaStream_t)stream), "pls_cv_shard_pick_f64");
+  return check_cuda(ctx, pls::cv_shard_pick(candidates, world, slot, d, m, threshold, has_threshold, tie_mode, forced != 0, n_local,
+                                            n_offset, scratch, indices_out, (cudaStream_t)stream), "pls_cv_shard_pick_f64");
 }
 
 int pls_cv_shard_update_f64(pls_ctx* ctx, int kernel_id, const double* xa_local, int64_t n_local, int64_t n_offset, int d, int iter,
@@ -414,10 +491,29 @@ int pls_cv_shard_update_f64(pls_ctx* ctx, int kernel_id, const double* xa_local,
                                               (cudaStream_t)stream), "pls_cv_shard_update_f64");
 }
 
+int pls_cv_shard_force_f64(pls_ctx* ctx, const double* xa_local, int64_t n_local, int64_t n_offset, int d, int m, int slot,
+                           int64_t pivot, const double* ci, const double* di, double* scratch, double* candidate, void* stream) {
+  if (!ctx) return 1;
+  if (slot < 1 || slot >= m || pivot < 0 || n_local < 0 || d < 1 || d > pls::MAX_D || !scratch || !candidate ||
+      (n_local > 0 && (!xa_local || !ci || !di)))
+    return fail(ctx, "pls_cv_shard_force_f64: bad arguments");
+  return check_cuda(ctx, pls::cv_shard_force(xa_local, n_local, n_offset, d, m, slot, pivot, ci, di, scratch, candidate,
+                                             (cudaStream_t)stream), "pls_cv_shard_force_f64");
+}
+
+int pls_cv_shard_status(pls_ctx* ctx, const double* scratch, int64_t* status4, void* stream) {
+  if (!ctx) return 1;
+  if (!scratch || !status4) return fail(ctx, "pls_cv_shard_status: NULL argument");
+  return check_cuda(ctx, pls::cv_shard_status(scratch, status4, (cudaStream_t)stream), "pls_cv_shard_status");
+}
+
 int pls_cv_shard_finish(pls_ctx* ctx, const double* scratch, int* n_selected_out, void* stream) {
   if (!ctx) return 1;
   if (!scratch || !n_selected_out) return fail(ctx, "pls_cv_shard_finish: NULL argument");
-  return check_cuda(ctx, pls::cv_shard_finish(scratch, n_selected_out, (cudaStream_t)stream), "pls_cv_shard_finish");
+  int64_t st[4];
+  if (check_cuda(ctx, pls::cv_shard_status(scratch, st, (cudaStream_t)stream), "pls_cv_shard_finish")) return 1;
+  *n_selected_out = (int)st[0];
+  return 0;
 }
 
 }  // extern "C"

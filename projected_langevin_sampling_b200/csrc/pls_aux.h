@@ -58,20 +58,22 @@ cudaError_t launch_flat_math(int op, const double* a, const double* b, int64_t n
 cudaError_t launch_gram_exp(const double* x, int64_t n, int fast, double* out, cudaStream_t stream);
 
 // ConditionalVariance selector (pls_selector.cu)
-int64_t cv_scratch_doubles(int64_t n);
+int64_t cv_scratch_doubles(int64_t n, int d, int m);
 cudaError_t run_cv_select(const pls_ctx* ctx, int kernel_id, const double* xp_aug, int64_t n, int d, double kdiag, int m,
-                          double jitter, double threshold, int has_threshold, double* ci, double* di, double* scratch,
-                          int64_t* indices_out, int* n_selected_out, cudaStream_t stream);
+                          double jitter, double threshold, int has_threshold, int tie_mode, pls_cv_tie_fn tie_fn, void* tie_user,
+                          double* ci, double* di, double* scratch, int64_t* indices_out, int* n_selected_out, cudaStream_t stream);
 
 // row-sharded selector (one candidate record per rank and pivot; the host all-gathers the records between the calls)
 int64_t cv_shard_scratch_doubles(int64_t n_local, int d, int m);
 int64_t cv_candidate_doubles(int d, int m);
 cudaError_t cv_shard_begin(int kernel_id, const double* xa, int64_t n_local, int64_t n_offset, int d, double kdiag, int m,
                            double jitter, double* di, double* scratch, double* cand, cudaStream_t stream);
-cudaError_t cv_shard_pick(const double* cands, int world, int slot, int d, int m, double threshold, int has_threshold,
-                          int64_t n_local, int64_t n_offset, double* scratch, int64_t* indices, cudaStream_t stream);
+cudaError_t cv_shard_pick(const double* cands, int world, int slot, int d, int m, double threshold, int has_threshold, int tie_mode,
+                          int forced, int64_t n_local, int64_t n_offset, double* scratch, int64_t* indices, cudaStream_t stream);
 cudaError_t cv_shard_update(int kernel_id, const double* xa, int64_t n_local, int64_t n_offset, int d, int iter, int m,
                             double jitter, double* ci, double* di, double* scratch, double* cand, cudaStream_t stream);
-cudaError_t cv_shard_finish(const double* scratch, int* n_selected_out, cudaStream_t stream);
+cudaError_t cv_shard_force(const double* xa, int64_t n_local, int64_t n_offset, int d, int m, int slot, int64_t pivot,
+                           const double* ci, const double* di, double* scratch, double* cand, cudaStream_t stream);
+cudaError_t cv_shard_status(const double* scratch, int64_t* status4, cudaStream_t stream);
 
 }  // namespace pls

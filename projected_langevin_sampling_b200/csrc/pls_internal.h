@@ -4,6 +4,7 @@
 #include <stdint.h>
 
 #include <string>
+#include <vector>
 
 #include "../../include/pls_b200.h"
 
@@ -16,6 +17,14 @@ struct pls_ctx {
   const uint64_t* step_counter = nullptr;  // device counter added to pls_project_update_f64's `step` (pls_set_step_counter)
   int tile_rt = 0;  // 0 = choose per launch from the particle count; 1 / 2 force a tile shape (PLS_B200_TILE_RT, tests)
   std::string error;
+  // pls_profile_begin / pls_profile_end: CUDA-event pairs around every launch of the hot kernel (role 0 forward, 1 backward)
+  struct ProfileRecord {
+    int role;
+    double flops;
+    cudaEvent_t e0, e1;
+  };
+  bool profiling = false;
+  std::vector<ProfileRecord> profile;
 };
 
 namespace pls {

@@ -19,6 +19,7 @@ FP64 pipe (+9 % at the headline shape for 8.2 GB).
 """
 from __future__ import annotations
 
+import ctypes as C
 import os
 from typing import Callable, List, Optional, Tuple, Union
 
@@ -75,27 +76,52 @@ class LangevinEngine:
         self._gram_staged = gram_staged and gram is None
         self.gaussian_normal_equations = gaussian_normal_equations  # opt-in, see _normal_equations()
         self._neq = None  # (key, A' in Gram-cache layout, b', y^T y / (2 s))
+        self._neq_y: Optional[torch.Tensor] = None
         self.xa, self.za, self.vt, self.inv_lambda = xa, za, vt, inv_lambda
         self.n, self.m, self.m_k, self.j = xa.shape[0], za.shape[0], vt.shape[1], j
         self.gradient_reduce = gradient_reduce
         self.weights_fn = weights_fn  # fills W (M x J) from the particles; default W = V~ P (OrthonormalBasis)
         dev = xa.device
-        self.ldj = ops.even(j)
-        rows = max(ROW_ALIGN, (dc_budget_bytes // (self.ldj * 8)) // ROW_ALIGN * ROW_ALIGN)
-        self.chunk_rows = min(self.n, rows)
-        self.chunks: List[Tuple[int, int]] = [(r, min(r + self.chunk_rows, self.n)) for r in range(0, self.n, self.chunk_rows)]
-        self.w = torch.zeros((self.m, self.ldj), dtype=torch.float64, device=dev)
-        self.gm = torch.zeros((self.m, self.ldj), dtype=torch.float64, device=dev)
-        self.dc = torch.zeros((self.chunk_rows, self.ldj), dtype=torch.float64, device=dev)
-        if self._gram_staged and self.n > 0:
-            self.kstage = torch.zeros((int(ctx.lib.pls_gram_cache_rows(self.chunk_rows)), int(ctx.lib.pls_gram_cache_ld(self.m))),
-                                      dtype=torch.float64, device=dev)
-        self.splits = ops.backward_splits(ctx, self.chunk_rows, self.m, j)
-        self.gp = torch.zeros((self.splits, self.m, self.ldj), dtype=torch.float64, device=dev)
-        self.cost_partial: Optional[torch.Tensor] = None  # (row tiles, ldj), allocated by the first gradient(with_cost=True)
+        self.dc_budget_bytes = int(dc_budget_bytes)
+        self._gram_code = nat.GRAM_CACHED if gram is not None else (nat.GRAM_STAGED if self._gram_staged and self.n > 0 else nat.GRAM_GENERATED)
+        self._plan_workspace(with_cost=False)
         self._neq_cost: Optional[torch.Tensor] = None
-        self.tile_rows = 0
         self._zeros: Optional[torch.Tensor] = None
+        self._cost_sums: Optional[torch.Tensor] = None
+
+    def _plan_workspace(self, with_cost: bool) -> None:
+        """pls_step_plan_f64 fixes the row chunking and the workspace layout; ONE torch allocation backs W, G', the Dc chunk,
+        the split partials, the cost-sum region (only once an energy has been asked for: 0.5 GB at the headline shape) and the
+        Gram staging chunk.  The tensors below are views into it (the piecewise entry points and the tests use them)."""
+        ctx, dev = self.ctx, self.xa.device
+        plan = nat.StepPlan()
+        if ctx.lib.pls_step_plan_f64(ctx.handle, self.n, self.m, self.m_k, self.j, self.dc_budget_bytes, self._gram_code, int(with_cost),
+                                     C.byref(plan)) != 0:
+            raise ValueError(f"pls_step_plan_f64 rejected the shape N={self.n} M={self.m} M_k={self.m_k} J={self.j}")
+        self.plan = plan
+        self.ldj = int(plan.ldj)
+        self.chunk_rows = int(plan.chunk_rows)
+        self.chunks: List[Tuple[int, int]] = [(r, min(r + self.chunk_rows, self.n)) for r in range(0, self.n, max(self.chunk_rows, 1))]
+        self.splits = int(plan.splits)
+        self.tile_rows = int(plan.tile_rows)
+        self.workspace = torch.zeros((int(plan.workspace_bytes) // 8,), dtype=torch.float64, device=dev)
+        assert self.workspace.data_ptr() % 256 == 0
+
+        def view(offset: int, rows: int, cols: int) -> torch.Tensor:
+            return self.workspace[offset // 8: offset // 8 + rows * cols].view(rows, cols)
+
+        self.w = view(plan.off_w, self.m, self.ldj)
+        self.gm = view(plan.off_gm, self.m, self.ldj)
+        self.dc = view(plan.off_dc, max(self.chunk_rows, 1), self.ldj)[: self.chunk_rows]
+        self.gp = view(plan.off_gp, self.splits * self.m, self.ldj).view(self.splits, self.m, self.ldj)
+        self.cost_partial = view(plan.off_cost_partial, max(int(plan.cost_tiles), 1), self.ldj) if with_cost else None
+        self.kstage = None
+        if self._gram_code == nat.GRAM_STAGED:
+            self.kstage = view(plan.off_kstage, int(ctx.lib.pls_gram_cache_rows(self.chunk_rows)), int(ctx.lib.pls_gram_cache_ld(self.m)))
+
+    def _launches_per_gradient(self, with_cost: bool) -> int:
+        per_chunk = 2 + (1 if self._gram_code == nat.GRAM_STAGED else 0)
+        return (1 if self.weights_fn is None else 0) + (per_chunk * len(self.chunks) + 1 + (1 if with_cost else 0) if self.n > 0 else 1)
 
     # ---- pieces ------------------------------------------------------------------------------------------------------
     def _gram(self, r0: int = 0) -> Optional[torch.Tensor]:
@@ -110,32 +136,26 @@ class LangevinEngine:
     def gradient(self, particles: torch.Tensor, cost: nat.PlsCost, y: torch.Tensor, with_cost: bool = False) -> torch.Tensor:
         """G' = k(Z, X) d_2 c(y, k(X, Z) V~ P)  -> (M, ldj) workspace view.  with_cost also leaves the per-row-tile cost
         sums of the SAME forward pass in self.cost_partial (the energy potential costs no second forward)."""
-        self._weights(particles)
         if self.gaussian_normal_equations and self._is_gaussian_identity(cost):
+            self._weights(particles)
             return self._gradient_normal_equations(cost, y, with_cost)
         self._neq_cost = None
         if with_cost and self.cost_partial is None:
-            self.tile_rows = ops.forward_tile_rows(self.ctx, self.j)
-            tiles = sum((r1 - r0 + self.tile_rows - 1) // self.tile_rows for r0, r1 in self.chunks)
-            self.cost_partial = torch.zeros((tiles, self.ldj), dtype=torch.float64, device=self.xa.device)
-        t0 = 0
-        for ci, (r0, r1) in enumerate(self.chunks):
-            dc = self.dc[: r1 - r0]
-            if self.kstage is not None:
-                gram = ops.gram_fill(self.ctx, self.kernel_id, self.xa[r0:r1], self.za, self.d, self.kstage)
-            else:
-                gram = self._gram(r0)
-            if with_cost:
-                t1 = t0 + (r1 - r0 + self.tile_rows - 1) // self.tile_rows
-                ops.forward_step(self.ctx, self.kernel_id, self.xa[r0:r1], self.za, self.d, self.w, self.j, cost, y[r0:r1], dc,
-                                 self.cost_partial[t0:t1], gram=gram)
-                t0 = t1
-            else:
-                ops.forward(self.ctx, self.kernel_id, self.xa[r0:r1], self.za, self.d, self.w, self.j, nat.EPI_COST_DERIVATIVE,
-                            dc, cost=cost, y=y[r0:r1], gram=gram)
-            ops.backward(self.ctx, self.kernel_id, self.za, self.xa[r0:r1], self.d, dc, self.j, self.gp, self.splits,
-                         accumulate=ci > 0, gram=gram)
-        ops.reduce_splits(self.ctx, self.gp, self.j, self.gm)
+            self._plan_workspace(with_cost=True)
+        ctx = self.ctx
+        if self.weights_fn is not None:
+            self.weights_fn(particles, self.w)  # e.g. W = k(Z, Z)^{-1} P for the InducingPointBasis
+            vt_ptr, ldv, p_src = None, 0, self.w
+        else:
+            vt_ptr, ldv, p_src = self.vt.data_ptr(), ops._ld(self.vt), particles
+        if with_cost and self._cost_sums is None:
+            self._cost_sums = torch.zeros((self.j,), dtype=torch.float64, device=self.xa.device)
+        # one call: W = V~ P, the row-chunk loop (forward with the cost epilogue, backward), the split reduction (pls_grad_f64)
+        ctx.check(ctx.lib.pls_grad_f64(ctx.handle, C.byref(self.plan), self.kernel_id, self.d, self.xa.data_ptr(), self.za.data_ptr(),
+                                       vt_ptr, ldv, p_src.data_ptr(), ops._ld(p_src), C.byref(cost), nat.ptr(y),
+                                       nat.ptr(self.gram), ops._ld(self.gram) if self.gram is not None else 0,
+                                       self.workspace.data_ptr(), self._cost_sums.data_ptr() if with_cost else None, ctx.stream()))
+        ctx.launches += self._launches_per_gradient(with_cost)
         if self.gradient_reduce is not None:
             self.gradient_reduce(self.gm)
         return self.gm
@@ -153,9 +173,12 @@ class LangevinEngine:
         step costs 2 M^2 J flops instead of 4 N M J.  This is a re-association of the reference's algebra
         (orthonormal.py:98-108,151-158 with costs/gaussian.py:75-88), exact up to round-off, NOT the general path: bench.py's
         headline never uses it."""
-        key = (y.data_ptr(), y.shape[0], float(cost.observation_noise))
-        if self._neq is not None and self._neq[0] == key:
+        # keyed on the label tensor's identity AND its version counter (an in-place edit of y bumps it); the entry keeps a
+        # reference to y so the allocator cannot hand the same address to a different label tensor while the entry lives
+        key = (y.data_ptr(), y.shape[0], y._version, float(cost.observation_noise))
+        if self._neq is not None and self._neq[0] == key and self._neq_y is y:
             return self._neq
+        self._neq_y = y
         ctx, m, dev = self.ctx, self.m, self.xa.device
         s_obs = float(cost.observation_noise)
         a_pad = torch.zeros((int(ctx.lib.pls_gram_cache_rows(m)), int(ctx.lib.pls_gram_cache_ld(m))), dtype=torch.float64, device=dev)
@@ -199,6 +222,19 @@ class LangevinEngine:
     def step(self, particles: torch.Tensor, eta: float, cost: nat.PlsCost, y: torch.Tensor, out: torch.Tensor,
              noise_mode: int, xi: Optional[torch.Tensor] = None, seed: int = 0, step_index: int = 0,
              j_global_offset: int = 0, in_place: bool = False) -> torch.Tensor:
+        if self.gradient_reduce is None and self.weights_fn is None and not (self.gaussian_normal_equations and self._is_gaussian_identity(cost)):
+            # single GPU / particle-sharded: the whole step is ONE C call (pls_step_f64)
+            ctx = self.ctx
+            ctx.check(ctx.lib.pls_step_f64(ctx.handle, C.byref(self.plan), self.kernel_id, self.d, self.xa.data_ptr(), self.za.data_ptr(),
+                                           self.vt.data_ptr(), ops._ld(self.vt), self.inv_lambda.data_ptr(), particles.data_ptr(),
+                                           ops._ld(particles), C.byref(cost), nat.ptr(y), nat.ptr(self.gram),
+                                           ops._ld(self.gram) if self.gram is not None else 0, float(eta), noise_mode, nat.ptr(xi),
+                                           ops._ld(xi) if xi is not None else 0, seed & (2**64 - 1), step_index & (2**64 - 1),
+                                           j_global_offset, int(in_place), out.data_ptr(), ops._ld(out), None,
+                                           self.workspace.data_ptr(), ctx.stream()))
+            ctx.launches += self._launches_per_gradient(False) + 1
+            self._neq_cost = None
+            return out
         gm = self.gradient(particles, cost, y)
         return ops.project_update(self.ctx, self.vt, gm, particles, self.j, self.inv_lambda, eta, out, noise_mode=noise_mode,
                                   xi=xi, seed=seed, step=step_index, j_global_offset=j_global_offset, in_place=in_place)
@@ -209,12 +245,11 @@ class LangevinEngine:
         self.gradient(particles, cost, y, with_cost=True)
         if self._neq_cost is not None:  # Gaussian shortcut: the cost sums are complete on every rank already
             return ops.energy_terms(self.ctx, self._neq_cost.reshape(1, -1).contiguous(), self.j, particles, self.inv_lambda)
-        if self.gradient_reduce is None:
-            return ops.energy_terms(self.ctx, self.cost_partial, self.j, particles, self.inv_lambda)
-        # rows are sharded: the cost sums are partial over this rank's rows (summed over the row group), the prior term is not
-        c = ops.energy_terms(self.ctx, self.cost_partial, self.j, None, None)
-        self.gradient_reduce(c)
-        return c + ops.energy_terms(self.ctx, self._zero_row(), self.j, particles, self.inv_lambda)
+        c = self._cost_sums  # sum_n c(y_n, F[n][j]) of the SAME forward pass, written by pls_grad_f64
+        if self.gradient_reduce is not None:  # rows are sharded: the cost sums are partial over this rank's rows, the prior term is not
+            c = c.clone()
+            self.gradient_reduce(c)
+        return ops.energy_terms(self.ctx, c.reshape(1, -1), self.j, particles, self.inv_lambda)
 
     def _zero_row(self) -> torch.Tensor:
         if self._zeros is None:

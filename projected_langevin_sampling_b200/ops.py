@@ -241,21 +241,72 @@ def flat_math(ctx: nat.Context, op: int, a: torch.Tensor, b: Optional[torch.Tens
     return out
 
 
+def numpy_tie_rule(di, chosen) -> int:
+    """The reference's choice among exactly tied conditional variances, verbatim: the last entry of numpy's DEFAULT (unstable)
+    argsort of d that has not been chosen yet (src/inducing_point_selectors/conditional_variance.py:105-109).  Runs on the host
+    copy of d the selector hands over when -- and only when -- the maximum is attained by several points."""
+    import numpy as np
+
+    taken = set(int(c) for c in chosen)
+    for next_idx in reversed(np.argsort(di)):
+        if int(next_idx) not in taken:
+            return int(next_idx)
+    return -1
+
+
+TIE_RULES = ("numpy", "stable")
+
+
+def _tie_mode(tie_rule) -> int:
+    if callable(tie_rule) or tie_rule == "numpy":
+        return nat.CV_TIES_HOST
+    if tie_rule == "stable":
+        return nat.CV_TIES_HIGHEST_INDEX
+    raise ValueError(f"tie_rule must be one of {TIE_RULES} or a callable (d, chosen) -> index, got {tie_rule!r}")
+
+
 def cv_select(ctx: nat.Context, kernel_id: int, xp_aug: torch.Tensor, d: int, kdiag: float, m: int, jitter: float,
-              threshold: Optional[float]) -> Tuple[torch.Tensor, int]:
-    """Returns (indices into the permuted order (m,), number selected)."""
+              threshold: Optional[float], tie_rule="numpy", info: Optional[dict] = None) -> Tuple[torch.Tensor, int]:
+    """Returns (indices into the permuted order (m,), number selected).
+    tie_rule: "numpy" (default: exact ties are resolved on the host by numpy_tie_rule, i.e. as the reference does), "stable"
+    (highest permuted index, decided on the device) or a callable (d_host: np.ndarray, chosen: np.ndarray) -> index.
+    info (optional dict) receives min_top2_rel_gap, tied_picks and host_tie_calls."""
+    import numpy as np
+
     n = xp_aug.shape[0]
     dev = xp_aug.device
     ci = torch.empty((m - 1, n), dtype=F64, device=dev)
     di = torch.empty((n,), dtype=F64, device=dev)
-    scratch = torch.zeros((int(ctx.lib.pls_cv_scratch_doubles(n)),), dtype=F64, device=dev)
+    scratch = torch.zeros((int(ctx.lib.pls_cv_scratch_doubles(n, d, m)),), dtype=F64, device=dev)
     indices = torch.full((m,), n, dtype=torch.int64, device=dev)  # sentinel N, as conditional_variance.py:63
     nsel = C.c_int(0)
-    ctx.check(ctx.lib.pls_cv_select_f64(ctx.handle, kernel_id, xp_aug.data_ptr(), n, d, float(kdiag), m, float(jitter),
-                                        float(threshold) if threshold is not None else 0.0, int(threshold is not None),
-                                        ci.data_ptr(), di.data_ptr(), scratch.data_ptr(), indices.data_ptr(),
-                                        C.byref(nsel), ctx.stream()))
+    mode = _tie_mode(tie_rule)
+    rule = tie_rule if callable(tie_rule) else numpy_tie_rule
+    calls, failure = [0], []
+
+    def on_tie(_user, d_host, n_host, chosen, n_chosen):
+        try:
+            calls[0] += 1
+            d_arr = np.ctypeslib.as_array(d_host, shape=(int(n_host),))
+            c_arr = np.ctypeslib.as_array(chosen, shape=(int(n_chosen),)) if n_chosen else np.zeros((0,), dtype=np.int64)
+            return int(rule(d_arr, c_arr))
+        except BaseException as exc:  # an exception must not unwind through the C frames
+            failure.append(exc)
+            return -1
+
+    callback = nat.CV_TIE_FN(on_tie)
+    rc = ctx.lib.pls_cv_select_f64(ctx.handle, kernel_id, xp_aug.data_ptr(), n, d, float(kdiag), m, float(jitter),
+                                   float(threshold) if threshold is not None else 0.0, int(threshold is not None), mode, callback,
+                                   None, ci.data_ptr(), di.data_ptr(), scratch.data_ptr(), indices.data_ptr(), C.byref(nsel),
+                                   ctx.stream())
+    if failure:
+        raise failure[0]
+    ctx.check(rc)
     ctx.launches += 2 * m
+    if info is not None:
+        hdr = scratch[: nat.CV_HEADER_DOUBLES].cpu()
+        info.update(min_top2_rel_gap=float(hdr[8]), tied_picks=int(hdr.view(torch.int64)[9]), host_tie_calls=calls[0],
+                    trace=float(hdr[4]))
     return indices, int(nsel.value)
 
 
@@ -263,11 +314,14 @@ class ShardedSelectorState:
     """One rank's workspaces of the row-sharded ConditionalVariance selector (pls_cv_shard_*)."""
 
     def __init__(self, ctx: nat.Context, kernel_id: int, xa_local: torch.Tensor, n_offset: int, n_total: int, d: int, kdiag: float,
-                 m: int, jitter: float, threshold: Optional[float]):
+                 m: int, jitter: float, threshold: Optional[float], tie_rule="numpy"):
         self.ctx, self.kernel_id, self.xa, self.n_offset, self.d, self.m = ctx, kernel_id, xa_local, int(n_offset), d, m
         self.kdiag, self.jitter = float(kdiag), float(jitter)
         self.threshold, self.has_threshold = (float(threshold), 1) if threshold is not None else (0.0, 0)
+        self.tie_mode = _tie_mode(tie_rule)
+        self.tie_rule = tie_rule if callable(tie_rule) else numpy_tie_rule
         self.n_local = xa_local.shape[0]
+        self.n_total = int(n_total)
         dev = xa_local.device
         self.ci = torch.empty((m - 1, max(self.n_local, 1)), dtype=F64, device=dev)
         self.di = torch.empty((max(self.n_local, 1),), dtype=F64, device=dev)
@@ -284,12 +338,12 @@ class ShardedSelectorState:
         c.launches += 2
         return self.candidate
 
-    def pick(self, candidates: torch.Tensor, slot: int) -> None:
+    def pick(self, candidates: torch.Tensor, slot: int, forced: bool = False) -> None:
         c = self.ctx
         world = candidates.numel() // self.record
         c.check(c.lib.pls_cv_shard_pick_f64(c.handle, candidates.data_ptr(), world, slot, self.d, self.m, self.threshold,
-                                            self.has_threshold, self.n_local, self.n_offset, self.scratch.data_ptr(),
-                                            self.indices.data_ptr(), c.stream()))
+                                            self.has_threshold, self.tie_mode, int(forced), self.n_local, self.n_offset,
+                                            self.scratch.data_ptr(), self.indices.data_ptr(), c.stream()))
         c.launches += 1
 
     def update(self, iteration: int) -> torch.Tensor:
@@ -300,6 +354,22 @@ class ShardedSelectorState:
         c.launches += 2
         return self.candidate
 
+    def force(self, slot: int, pivot: int) -> torch.Tensor:
+        """The candidate record of the point with GLOBAL permuted index `pivot` (an empty record on the ranks that do not hold it)."""
+        c = self.ctx
+        c.check(c.lib.pls_cv_shard_force_f64(c.handle, self.xa.data_ptr(), self.n_local, self.n_offset, self.d, self.m, slot, int(pivot),
+                                             self.ci.data_ptr(), self.di.data_ptr(), self.scratch.data_ptr(), self.candidate.data_ptr(),
+                                             c.stream()))
+        c.launches += 1
+        return self.candidate
+
+    def status(self) -> Tuple[int, bool, bool, int]:
+        """(n_selected, stopped, tie pending, slot of the tie); synchronises."""
+        c = self.ctx
+        st = (C.c_int64 * 4)()
+        c.check(c.lib.pls_cv_shard_status(c.handle, self.scratch.data_ptr(), st, c.stream()))
+        return int(st[0]), bool(st[1]), bool(st[2]), int(st[3])
+
     def finish(self) -> int:
         c = self.ctx
         nsel = C.c_int(0)
@@ -307,17 +377,45 @@ class ShardedSelectorState:
         return int(nsel.value)
 
 
-def cv_select_sharded(states: Sequence[ShardedSelectorState], gather) -> Tuple[torch.Tensor, int]:
+def cv_select_sharded(states: Sequence[ShardedSelectorState], gather, gather_d=None) -> Tuple[torch.Tensor, int]:
     """Drives the sharded selector.  `states` are the ranks handled by THIS process (one in production; several when a
     test emulates the ranks on one GPU); `gather(list of this process's candidate records)` returns all ranks' records
-    concatenated in rank order (torch.distributed.all_gather_into_tensor in production)."""
+    concatenated in rank order (torch.distributed.all_gather_into_tensor in production).  `gather_d(list of this process's
+    slices of d)` returns the WHOLE d (all ranks, rank order) as a host numpy array; it is called only when the maximum is
+    attained by several points and the tie rule is the host's (every rank then applies the same rule to the same array)."""
     m = states[0].m
+    host_ties = states[0].tie_mode == nat.CV_TIES_HOST
     cands = gather([s.begin() for s in states])
     for s in states:
         s.pick(cands, 0)
-    for i in range(m - 1):
-        cands = gather([s.update(i) for s in states])
-        for s in states:
-            s.pick(cands, i + 1)
+    i, batch = 0, (8 if host_ties else m)
+    while i < m - 1:
+        end = min(m - 1, i + batch)
+        while i < end:
+            cands = gather([s.update(i) for s in states])
+            for s in states:
+                s.pick(cands, i + 1)
+            i += 1
+        if not host_ties:
+            break
+        _, stopped, tie, slot = states[0].status()
+        if tie:
+            if gather_d is None:
+                raise RuntimeError("cv_select_sharded: a tie has to be resolved on the host but no gather_d was given")
+            d_host = gather_d([s.di[: s.n_local] for s in states])
+            chosen = states[0].indices[:slot].cpu().numpy()
+            pivot = int(states[0].tie_rule(d_host, chosen))
+            if pivot < 0 or pivot >= states[0].n_total or pivot in set(chosen.tolist()):
+                raise RuntimeError(f"cv_select_sharded: the tie rule returned {pivot}, which is out of range or already chosen")
+            cands = gather([s.force(slot, pivot) for s in states])
+            for s in states:
+                s.pick(cands, slot, forced=True)
+            if stopped:
+                break
+            i, batch = slot, 1
+        else:
+            if stopped:
+                break
+            batch = min(2 * batch, 64)
     nsel = [s.finish() for s in states]
     return states[0].indices, nsel[0]

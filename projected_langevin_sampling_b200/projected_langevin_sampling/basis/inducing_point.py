@@ -5,7 +5,10 @@ The two N-sized contractions are the same generated-operand kernels as the Ortho
 W = k(Z, Z)^{-1} P, pls_backward_f64 for k(Z, X) Dc): k(X, Z) and the (N, J) prediction are never materialised in the fused
 step.  The M x M pieces follow the reference: `gpytorch.solve(k(Z, Z), .)` is a Cholesky solve (gpytorch's choice up to
 M = 800; above that it switches to CG with a loose tolerance, so parity is only well-defined for M <= 800) with the factor
-computed once on the host in float64; the N(0, k(Z, Z)) noise is V sqrt(clip(lambda, 0)) z with the eigendecomposition
+computed once on the host in float64 (`psd_safe_cholesky`: the same jitter retries when k(Z, Z) is numerically indefinite;
+the per-step solve stays `torch.cholesky_solve` = cuSOLVER potrs, 2 M^2 J flops of library TRSM against the step's 4 N M J --
+for M <= 800 that is < 0.1 % of a step at any N >= 100 M, so a hand-written triangular solve would buy nothing measurable and
+would have to reproduce potrs's rounding to keep the 1e-10 parity with the reference's own Cholesky solve); the N(0, k(Z, Z)) noise is V sqrt(clip(lambda, 0)) z with the eigendecomposition
 computed once (the reference recomputes it every step, samplers.py:6-44) and z the reference's torch.normal((M, J)) draw.
 """
 from __future__ import annotations
@@ -21,6 +24,30 @@ from ...engine import DEFAULT_DC_BUDGET, LangevinEngine, gram_mode, want_gram_ca
 from ...kernels import dense_gram, kernel_spec
 from ...samplers import langevin_noise, sample_multivariate_normal
 from .base import PLSBasis
+
+
+def psd_safe_cholesky(a: torch.Tensor, max_tries: int = 3) -> torch.Tensor:
+    """What `gpytorch.solve` factorises with (linear_operator.utils.cholesky.psd_safe_cholesky, the path taken by
+    basis/inducing_point.py:104-106,141-143 for M <= 800): plain Cholesky first; if the matrix is numerically indefinite, retry
+    with a growing diagonal jitter -- 1e-8 in float64, times 10 per retry (gpytorch's cholesky_jitter default for double,
+    cholesky_max_tries = 3) -- and raise only when the last retry fails.  A warning reports the jitter that was needed."""
+    import warnings
+
+    l, info = torch.linalg.cholesky_ex(a)
+    if not bool(info.any()):
+        return l
+    if bool(torch.isnan(a).any()):
+        raise ValueError(f"cholesky: {int(torch.isnan(a).sum())} of {a.numel()} elements of the {tuple(a.shape)} matrix are NaN")
+    base, prev, a_j = 1e-8 if a.dtype == torch.float64 else 1e-6, 0.0, a.clone()
+    for i in range(max_tries):
+        jitter = base * (10**i)
+        a_j.diagonal().add_(jitter - prev)
+        prev = jitter
+        l, info = torch.linalg.cholesky_ex(a_j)
+        if not bool(info.any()):
+            warnings.warn(f"k(Z, Z) not positive definite: added jitter of {jitter:.1e} to the diagonal", RuntimeWarning)
+            return l
+    raise torch.linalg.LinAlgError(f"k(Z, Z) not positive definite after adding {prev:.1e} to the diagonal")
 
 
 class InducingPointBasis(PLSBasis):
@@ -48,7 +75,7 @@ class InducingPointBasis(PLSBasis):
         self.gram_induce = kernel.forward(x1=self.x_induce, x2=self.x_induce)  # r(Z, Z)   (:38-40)
         self.base_gram_induce = ops.gram(self.ctx, self._spec.kernel_id, za_plain, self._za, d)  # k(Z, Z)   (:41-43)
         k_host = self.base_gram_induce.cpu()
-        self._chol = torch.linalg.cholesky(k_host).to(dev)  # gpytorch.solve's Cholesky path
+        self._chol = psd_safe_cholesky(k_host).to(dev)  # gpytorch.solve's Cholesky path (with its jitter retries)
         lam, vec = torch.linalg.eigh(k_host)  # samplers.py:23-26, once
         self._noise_factor = (vec * torch.sqrt(torch.clip(lam, 0, None))[None, :]).to(dev).contiguous()  # V sqrt(lambda)
         self._m_over = torch.full((m,), float(m), dtype=torch.float64, device=dev)

@@ -52,9 +52,10 @@ class PLSCost(ABC):
     def y_device(self, device=None) -> torch.Tensor:
         """Training labels as a float64 CUDA vector (cached)."""
         dev = device or torch.device("cuda", torch.cuda.current_device())
-        if self._y_dev is None or self._y_dev.device != dev or self._y_src is not self.y_train:
+        version = getattr(self.y_train, "_version", 0)  # an in-place edit of y_train bumps it: the device copy is refreshed
+        if self._y_dev is None or self._y_dev.device != dev or self._y_src is not self.y_train or self._y_version != version:
             self._y_dev = ops.as_device_f64(self.y_train.reshape(-1), dev)
-            self._y_src = self.y_train
+            self._y_src, self._y_version = self.y_train, version
         return self._y_dev
 
     # ---- reference API -------------------------------------------------------------------------------------------------

@@ -67,6 +67,11 @@ class PLS:
     def step_(self, particles: torch.Tensor, step_size: float, noise=None, philox: Optional[Tuple[int, int, int]] = None) -> torch.Tensor:
         """In-place Langevin step: particles += delta, one fused launch sequence, no (M_k, J) temporary.
         philox=(seed, step_index, j_global_offset) uses the device-side noise stream (no host RNG, no H2D copy)."""
+        if not self._fused():  # a basis / cost without the fused path: the reference's two-call composition, applied in place
+            if philox is not None:
+                raise ValueError("philox noise needs the fused CUDA path (OrthonormalBasis / InducingPointBasis with a native cost)")
+            particles += self.calculate_particle_update(particles, step_size, noise=noise)
+            return particles
         return self.basis.fused_particle_update(particles, self.cost, float(step_size), noise=noise, in_place=True, philox=philox)
 
     def calculate_energy_potential(self, particles: torch.Tensor) -> float:

@@ -145,6 +145,33 @@ def selector_runs():
     print("selector:", idx.tolist()[:8], idx1.tolist()[:8])
 
 
+def scale_problem(n, d, seed=0):
+    """C4-style inputs (X ~ N(0, I), ARD lengthscales sqrt(D) (0.75 + 0.5 k / (D - 1))), regenerated from the
+    seed by the tests -- only the selected indices are stored."""
+    x = torch.randn(n, d, generator=torch.Generator().manual_seed(seed), dtype=torch.float64)
+    ls = torch.tensor([math.sqrt(d) * (0.75 + 0.5 * k / max(d - 1, 1)) for k in range(d)], dtype=torch.float64)
+    return x, ls
+
+
+def selector_scale(sizes=((100_000, 256), (1_000_000, 1024))):
+    """The reference's ConditionalVariance selector at C4-like scale (D = 8 ARD): N = 100 000, M = 256 and -- host memory
+    permitting (the reference's C is 8.2 GB) -- the C4 shape itself, N = 1 000 000, M = 1024.  Indices only."""
+    import time
+
+    path = os.path.join(HERE, "selector_scale.npz")
+    out = dict(np.load(path)) if os.path.exists(path) else {}
+    for n, m in sizes:
+        x, ls = scale_problem(n, 8)
+        kernel = make_kernel(ls, 1.0, ard=8)
+        set_seed(123)
+        t0 = time.time()
+        z, idx = ConditionalVarianceInducingPointSelector()(x=x, m=m, kernel=kernel)
+        tag = f"n{n}_m{m}"
+        out.update({tag + "_idx": idx.numpy(), tag + "_seed": 123, tag + "_data_seed": 0, tag + "_d": 8, tag + "_outputscale": 1.0})
+        print("selector_scale", tag, "reference run", round(time.time() - t0, 1), "s; first", idx.tolist()[:6], flush=True)
+        np.savez(path, **out)
+
+
 def train_loop_runs():
     """experiments/trainers.py:139-162 `train_pls` (the caller of the hot path) with experiments/early_stopper.py:4-24:
     one run that uses all its epochs and one that the EarlyStopper ends (energies appended only for accepted steps)."""
@@ -206,6 +233,7 @@ def ipb_runs():
 
 
 if __name__ == "__main__":
+    # selector_scale takes ~15 min and 10 GB of host memory: run it by name
     which = sys.argv[1:] or ["readme_demo", "one_step_all_costs", "selector_runs", "train_loop_runs", "ipb_runs"]
     for name in which:
         globals()[name]()

@@ -67,12 +67,12 @@ def test_config2_bernoulli_full(b200, gram_cache):
     x, y, g = _curve_inputs(n, "bernoulli")
     orc_kernel = RBFScaleKernel(torch.tensor([0.5], dtype=torch.float64), 1.0)
     kernel = b200.ScaleKernel(b200.RBFKernel(lengthscale=0.5), outputscale=1.0)
-    # selector: linspace inputs give exact ties, which the reference resolves with an unstable argsort; both sides use the
-    # stable rule here (see test_readme_demo_against_reference_run)
+    # selector: linspace inputs give exact ties; the selector resolves them as the reference does (numpy's default argsort on
+    # the host, for the tied iterations only), so it is compared with the oracle's literal restatement of :105-109
     b200.set_seed(0)
     z_sel, idx = b200.ConditionalVarianceInducingPointSelector()(x=x, m=24, kernel=kernel)
     oracle_set_seed(0)
-    z_orc, idx_orc, trace = conditional_variance_select(x, 24, orc_kernel, argsort_kind="stable", return_trace=True)
+    z_orc, idx_orc, trace = conditional_variance_select(x, 24, orc_kernel, return_trace=True)
     assert trace["di"].max() > 1e-9  # still above the round-off floor after 24 pivots
     assert idx.tolist() == idx_orc.tolist() and torch.equal(z_sel, z_orc)
     z = x[torch.linspace(0, n - 1, m).long()].clone()
@@ -230,3 +230,59 @@ def test_gaussian_normal_equations_shortcut(b200, gram_cache):
     _, ef = train_pls(fast, pf.clone(), number_of_epochs=6, step_size=1e-6, early_stopper_patience=1e9, philox_seed=11)
     _, eg = train_pls(general, pf.clone(), number_of_epochs=6, step_size=1e-6, early_stopper_patience=1e9, philox_seed=11)
     assert len(ef) == len(eg) == 6 and max(abs(a - b) / abs(b) for a, b in zip(ef, eg)) < TOL
+
+
+# ---- selector at C4-like scale against runs of the reference (tests/golden/make_golden.py::selector_scale) ----------------
+def _scale_problem(n, d, seed):
+    x = torch.randn(n, d, generator=torch.Generator().manual_seed(seed), dtype=torch.float64)
+    ls = torch.tensor([math.sqrt(d) * (0.75 + 0.5 * k / max(d - 1, 1)) for k in range(d)], dtype=torch.float64)
+    return x, ls
+
+
+@pytest.mark.parametrize("tag", ["n100000_m256", "n1000000_m1024"])
+def test_selector_at_scale_against_reference_run(b200, golden_dir, tag):
+    """N = 100 000, M = 256 and the C4 shape N = 1 000 000, M = 1024 (D = 8 ARD): the indices of the unmodified reference run
+    (numpy BLAS `np.dot(cj, ci[:i])` accumulation, torch CPU exp) against pls_cv_select_f64 (fixed-order FMA chain, CUDA exp) --
+    bit-exact -- together with the smallest relative top-2 gap met on the way (how far the selection was from depending on
+    round-off).  Then the row-sharded entry points (three uneven emulated ranks) on the same problem."""
+    import os
+
+    from projected_langevin_sampling_b200 import _native as nat, ops
+    from projected_langevin_sampling_b200.kernels import kernel_spec
+
+    g = np.load(os.path.join(golden_dir, "selector_scale.npz"))
+    if tag + "_idx" not in g:
+        pytest.skip(f"no reference run stored for {tag}")
+    n, m = (int(v[1:]) for v in tag.split("_"))
+    d = int(g[tag + "_d"])
+    x, ls = _scale_problem(n, d, int(g[tag + "_data_seed"]))
+    kernel = b200.ScaleKernel(b200.RBFKernel(ard_num_dims=d, lengthscale=ls), outputscale=float(g[tag + "_outputscale"]))
+    b200.set_seed(int(g[tag + "_seed"]))
+    sel = b200.ConditionalVarianceInducingPointSelector()
+    z, idx = sel(x=x, m=m, kernel=kernel)
+    want = g[tag + "_idx"]
+    agree = int((idx.numpy() == want).sum())
+    first_diff = int(np.argmax(idx.numpy() != want)) if agree < m else -1
+    info = sel.last_run_info
+    print(f"[selector {tag}] identical pivots {agree}/{m} (first difference at {first_diff}); min top-2 relative gap "
+          f"{info['min_top2_rel_gap']:.3e}; tied picks {info['tied_picks']}; host tie calls {info['host_tie_calls']}")
+    assert idx.tolist() == want.tolist()
+    assert torch.equal(z, x[torch.from_numpy(want)])
+    assert info["min_top2_rel_gap"] > 1e-12  # round-off of the two arithmetic orders is ~1e-15: the comparison is meaningful
+    del sel, z
+    torch.cuda.empty_cache()
+
+    # row-sharded entry points, ranks emulated on this GPU: same permutation, three uneven shards
+    ctx = nat.context()
+    b200.set_seed(int(g[tag + "_seed"]))
+    perm = np.random.permutation(n)
+    spec = kernel_spec(kernel, d)
+    centre = x.mean(dim=0).tolist()
+    bounds = [0, n // 3 + 17, 2 * n // 3 - 5, n]
+    states = []
+    for a, b in zip(bounds[:-1], bounds[1:]):
+        xa = ops.prepare_points(ctx, spec.kernel_id, x[torch.from_numpy(perm[a:b])].cuda(), spec.inv_lengthscale, centre, 0.5 * spec.log_outputscale)
+        states.append(ops.ShardedSelectorState(ctx, spec.kernel_id, xa, a, n, d, spec.outputscale, m, 1e-12, 0.0))
+    local, nsel = ops.cv_select_sharded(states, lambda recs: torch.cat(recs), lambda sl: torch.cat(sl).cpu().numpy())
+    assert nsel == m
+    assert perm[local.cpu().numpy()].tolist() == want.tolist()

@@ -197,26 +197,65 @@ def test_non_finite_cost_derivative_stays_in_its_column(ctx):
 
 @pytest.mark.parametrize("bounds", [[0, 1700, 3000], [0, 1, 1, 2999, 3000], [0, 3000]])
 @pytest.mark.parametrize("threshold", [0.0, 2400.0])
-def test_row_sharded_selector_equals_unsharded(ctx, bounds, threshold):
+@pytest.mark.parametrize("rule", ["numpy", "stable"])
+def test_row_sharded_selector_equals_unsharded(ctx, bounds, threshold, rule):
     """pls_cv_shard_* with the ranks emulated on one GPU (the all-gather is a concatenation): uneven shards, a one-row
-    shard and an EMPTY shard; the indices and the early-stop count must equal pls_cv_select_f64's."""
+    shard and an EMPTY shard; the indices and the early-stop count must equal pls_cv_select_f64's, under both tie rules
+    (duplicated points straddling the shards force ties: "numpy" gathers d and asks the host, "stable" decides by GLOBAL index)."""
     from projected_langevin_sampling_b200 import _native as nat, ops
 
     g = torch.Generator().manual_seed(17)
     n, d, m = 3000, 5, 40
     x = torch.randn(n, d, generator=g, dtype=torch.float64).cuda()
-    x[100] = x[2500]  # an exact duplicate: a tie that the GLOBAL-index rule must resolve identically across shards
+    x[:1000] = x[1700:2700]  # exact duplicates straddling the shards: whenever one of them is the maximum it is a 2-way tie
+    x[2999] = x[1]
     inv_ls = [0.5, 0.6, 0.7, 0.4, 0.45]
     centre = x.mean(0).tolist()
     xa = ops.prepare_points(ctx, nat.KERNEL_RBF, x, inv_ls, centre, 0.5 * float(np.log(1.3)))
-    want_idx, want_n = ops.cv_select(ctx, nat.KERNEL_RBF, xa, d, 1.3, m, 1e-12, threshold)
-    states = [ops.ShardedSelectorState(ctx, nat.KERNEL_RBF, xa[a:b].contiguous(), a, n, d, 1.3, m, 1e-12, threshold)
+    info = {}
+    want_idx, want_n = ops.cv_select(ctx, nat.KERNEL_RBF, xa, d, 1.3, m, 1e-12, threshold, tie_rule=rule, info=info)
+    states = [ops.ShardedSelectorState(ctx, nat.KERNEL_RBF, xa[a:b].contiguous(), a, n, d, 1.3, m, 1e-12, threshold, tie_rule=rule)
               for a, b in zip(bounds[:-1], bounds[1:])]
-    got_idx, got_n = ops.cv_select_sharded(states, lambda recs: torch.cat(recs))
+    gathered = []
+
+    def gather_d(slices):
+        gathered.append(1)
+        return torch.cat(slices).cpu().numpy()
+
+    got_idx, got_n = ops.cv_select_sharded(states, lambda recs: torch.cat(recs), gather_d)
     assert got_n == want_n and (threshold == 0.0) == (want_n == m)
     assert torch.equal(got_idx, want_idx)
+    assert len(gathered) == info["host_tie_calls"] and (rule == "stable") == (info["host_tie_calls"] == 0)
+    assert info["host_tie_calls"] + info["tied_picks"] >= 3  # the construction did produce ties
     for s in states[1:]:  # every rank ends with the same answer
         assert torch.equal(s.indices, got_idx)
+
+
+def test_selector_numpy_rule_against_cpu_restatement(ctx):
+    """Many-way exact ties (points on a 1-D grid with a short lengthscale, as the README demo) at a size where several batches
+    and several host decisions interleave: the indices equal a literal numpy restatement of conditional_variance.py:91-109 fed
+    with the kernel's own d (so only the tie handling is under test here, not round-off)."""
+    from projected_langevin_sampling_b200 import _native as nat, ops
+
+    n, m = 5000, 48
+    perm = np.random.default_rng(5).permutation(n)
+    x = torch.linspace(-4, 4, n, dtype=torch.float64)[perm][:, None].cuda()
+    xa = ops.prepare_points(ctx, nat.KERNEL_RBF, x, [1 / 0.07], [0.0], 0.0)
+    seen = []
+
+    def spy(dh, chosen):  # the reference's rule, recording what it was asked
+        seen.append((dh.copy(), chosen.copy()))
+        return ops.numpy_tie_rule(dh, chosen)
+
+    info = {}
+    idx, nsel = ops.cv_select(ctx, nat.KERNEL_RBF, xa, 1, 1.0, m, 1e-12, 0.0, tie_rule=spy, info=info)
+    idx = idx.cpu().numpy()
+    assert nsel == m and len(set(idx.tolist())) == m and len(seen) >= 5 and info["host_tie_calls"] == len(seen)
+    for dh, chosen in seen:  # each call was a genuine tie, and the pivot stored for that slot is the rule's answer
+        rest = np.delete(dh, chosen)
+        assert (rest == rest.max()).sum() > 1
+        assert idx[len(chosen)] == ops.numpy_tie_rule(dh, chosen)
+        assert idx[: len(chosen)].tolist() == chosen.tolist()
 
 
 def test_branch_free_epilogue_arithmetic_in_ulps(ctx):

@@ -233,17 +233,22 @@ def test_readme_demo_against_reference_run(b200, golden_dir):
         kernel = b200.ScaleKernel(b200.RBFKernel(lengthscale=float(g["lengthscale"])), outputscale=float(g["outputscale"]))
         # The README's linspace inputs produce EXACT ties in the conditional variances (every point further than ~6
         # lengthscales from the pivots keeps d = outputscale + jitter to the last bit).  The reference resolves them with
-        # numpy's default *unstable* argsort, i.e. implementation-defined (SIMD-dependent); the CUDA selector uses the
-        # stable rule (highest permuted index).  So: indices are compared with the oracle under the stable rule, and the
-        # Langevin run below starts from the inducing points the reference run itself selected.
+        # `reversed(np.argsort(d))`; the selector detects the ties on the device and asks the same numpy routine, so the
+        # indices are those of the reference run, and the Langevin run below starts from the points selected HERE.
         b200.set_seed(0)
-        z_sel, idx = b200.ConditionalVarianceInducingPointSelector()(x=x, m=10, kernel=kernel)
+        sel = b200.ConditionalVarianceInducingPointSelector()
+        z_sel, idx = sel(x=x, m=10, kernel=kernel)
+        assert idx.tolist() == g["induce_idx"].tolist()  # bit-exact indices, ties included
+        assert torch.equal(z_sel, torch.from_numpy(g["x_induce"]))
+        assert sel.last_run_info["host_tie_calls"] >= 1 and sel.last_run_info["min_top2_rel_gap"] == 0.0
+        # ... and the device-only rule (highest permuted index among tied points) equals the oracle with a stable argsort
+        b200.set_seed(0)
+        _, idx_s = b200.ConditionalVarianceInducingPointSelector(tie_rule="stable")(x=x, m=10, kernel=kernel)
         oracle_set_seed(0)
-        z_orc, idx_orc = conditional_variance_select(x, 10, RBFScaleKernel(float(g["lengthscale"]), float(g["outputscale"])),
-                                                     argsort_kind="stable")
-        assert idx.tolist() == idx_orc.tolist()
-        assert torch.equal(z_sel, z_orc)
-        z = torch.from_numpy(g["x_induce"])
+        _, idx_orc = conditional_variance_select(x, 10, RBFScaleKernel(float(g["lengthscale"]), float(g["outputscale"])),
+                                                 argsort_kind="stable")
+        assert idx_s.tolist() == idx_orc.tolist()
+        z = z_sel
         eig = (torch.from_numpy(g["eigenvalues"]), torch.from_numpy(g["eigenvectors"]))
         basis = b200.OrthonormalBasis(b200.PLSKernel(kernel, z), z, x, eigendecomposition=eig, verbose=False)
         # the package's own eigendecomposition agrees on the spectrum
@@ -267,20 +272,25 @@ def test_readme_demo_against_reference_run(b200, golden_dir):
 
 @pytest.mark.parametrize("tag", ["ard", "one"])
 def test_selector_against_reference_run(b200, tag, golden_dir):
-    """`ard`: generic 4-D inputs, no ties -> indices identical to the reference run.  `one`: 1-D inputs where every point
-    further than ~6 lengthscales from all pivots keeps d = outputscale + jitter to the last bit (exact ties), resolved by
-    numpy's unstable argsort in the reference; there the CUDA selector must equal the oracle under the stable rule and
-    every index it picks must be one the reference could have picked (maximal conditional variance)."""
+    """`ard`: generic 4-D inputs, no ties.  `one`: 1-D inputs where every point further than ~6 lengthscales from all pivots
+    keeps d = outputscale + jitter to the last bit (exact ties, which the reference resolves with numpy's default argsort and
+    the selector hands to the same routine).  Both: indices and points identical to the reference run."""
     g = np.load(os.path.join(golden_dir, "selector_runs.npz"))
     if tag == "one":
         x = torch.from_numpy(g["one_x"])
         kernel = b200.ScaleKernel(b200.RBFKernel(lengthscale=float(g["one_ls"])), outputscale=float(g["one_os"]))
         b200.set_seed(int(g["one_seed"]))
-        z, idx = b200.ConditionalVarianceInducingPointSelector()(x=x, m=int(g["one_m"]), kernel=kernel)
+        sel = b200.ConditionalVarianceInducingPointSelector()
+        z, idx = sel(x=x, m=int(g["one_m"]), kernel=kernel)
+        assert idx.tolist() == g["one_idx"].tolist()
+        assert torch.equal(z, torch.from_numpy(g["one_z"]))
+        assert sel.last_run_info["host_tie_calls"] >= 1
+        b200.set_seed(int(g["one_seed"]))
+        _, idx_s = b200.ConditionalVarianceInducingPointSelector(tie_rule="stable")(x=x, m=int(g["one_m"]), kernel=kernel)
         oracle_set_seed(int(g["one_seed"]))
-        zo, idxo = conditional_variance_select(x, int(g["one_m"]), RBFScaleKernel(float(g["one_ls"]), float(g["one_os"])),
-                                               argsort_kind="stable")
-        assert idx.tolist() == idxo.tolist() and torch.equal(z, zo)
+        _, idxo = conditional_variance_select(x, int(g["one_m"]), RBFScaleKernel(float(g["one_ls"]), float(g["one_os"])),
+                                              argsort_kind="stable")
+        assert idx_s.tolist() == idxo.tolist()
         return
     x = torch.from_numpy(g[f"{tag}_x"])
     ls = torch.as_tensor(g[f"{tag}_ls"]).reshape(-1)
@@ -439,17 +449,40 @@ def test_selector_matches_oracle_random(b200):
     assert torch.equal(z, zo)
 
 
-def test_selector_ties_follow_stable_rule(b200):
-    """Exact ties (duplicated rows): the CUDA selector picks the highest permuted index, = the oracle with a stable sort."""
+@pytest.mark.parametrize("rule", ["numpy", "stable"])
+def test_selector_ties_duplicated_rows(b200, rule):
+    """Exact ties from duplicated rows.  Default rule: the reference's `reversed(np.argsort(d))`, called on the host for the
+    tied iterations only (= the oracle's literal restatement).  "stable": the highest permuted index, on the device (= the
+    oracle with a stable sort)."""
     g = torch.Generator().manual_seed(2)
     base = torch.randn(40, 2, generator=g, dtype=torch.float64)
     x = torch.cat([base, base, base], dim=0)
     kernel = b200.ScaleKernel(b200.RBFKernel(ard_num_dims=2, lengthscale=1.0), outputscale=1.0)
     b200.set_seed(1)
-    _, idx = b200.ConditionalVarianceInducingPointSelector()(x=x, m=12, kernel=kernel)
+    sel = b200.ConditionalVarianceInducingPointSelector(tie_rule=rule)
+    _, idx = sel(x=x, m=12, kernel=kernel)
     oracle_set_seed(1)
-    _, idxo = conditional_variance_select(x, 12, RBFScaleKernel(1.0, 1.0), argsort_kind="stable")
+    _, idxo = conditional_variance_select(x, 12, RBFScaleKernel(1.0, 1.0), argsort_kind=None if rule == "numpy" else "stable")
     assert idx.tolist() == idxo.tolist()
+    assert sel.last_run_info["tied_picks"] + sel.last_run_info["host_tie_calls"] >= 1
+    assert (sel.last_run_info["host_tie_calls"] == 0) == (rule == "stable")
+
+
+def test_selector_custom_tie_rule_and_bad_rule(b200):
+    """A callable tie rule is honoured; one that returns an already chosen point is rejected loudly."""
+    x = torch.linspace(-1, 1, 200, dtype=torch.float64)[:, None]
+    kernel = b200.ScaleKernel(b200.RBFKernel(lengthscale=0.05), outputscale=1.0)
+    b200.set_seed(3)
+    lowest = lambda d, chosen: int(np.flatnonzero((d == np.delete(d, chosen).max()) & ~np.isin(np.arange(d.size), chosen))[0])  # noqa: E731
+    _, idx_low = b200.ConditionalVarianceInducingPointSelector(tie_rule=lowest)(x=x, m=6, kernel=kernel)
+    b200.set_seed(3)
+    _, idx_high = b200.ConditionalVarianceInducingPointSelector(tie_rule="stable")(x=x, m=6, kernel=kernel)
+    assert idx_low.tolist() != idx_high.tolist() and len(set(idx_low.tolist())) == 6
+    b200.set_seed(3)
+    with pytest.raises(Exception, match="already chosen|out of range"):
+        b200.ConditionalVarianceInducingPointSelector(tie_rule=lambda d, chosen: int(chosen[0]))(x=x, m=6, kernel=kernel)
+    with pytest.raises(ValueError):
+        b200.ConditionalVarianceInducingPointSelector(tie_rule="random")(x=x, m=6, kernel=kernel)
 
 
 def test_selector_early_stop_raises_like_reference(b200):

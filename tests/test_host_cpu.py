@@ -44,7 +44,9 @@ def test_layout_helpers():
     s = lib.pls_backward_splits(None, 1_000_000, 1024, 4096)
     assert (256 * s) % 148 == 0 and s >= 4
     assert lib.pls_backward_splits(None, 100, 10, 100) == 1  # tiny problems are not split
-    assert lib.pls_cv_scratch_doubles(1000) >= 8 + 3 * 4 + 125
+    # header + pivot record (SP + m) + 5 doubles per 256-row block + one taken byte per row + a candidate record
+    assert lib.pls_cv_scratch_doubles(1000, 8, 16) >= 16 + (12 + 16) + 5 * 4 + 125 + lib.pls_cv_candidate_doubles(8, 16)
+    assert lib.pls_cv_scratch_doubles(1000, 0, 16) == 0 and lib.pls_cv_scratch_doubles(1000, 8, 1) == 0
 
 
 def test_no_gpu_fails_loudly():
@@ -229,3 +231,43 @@ def test_gram_mode_argument_and_environment(monkeypatch):
     assert gram_mode(False) == "staged"
     monkeypatch.setenv("PLS_B200_GRAM_CACHE", "off")
     assert gram_mode(True) is False
+
+
+def test_psd_safe_cholesky_jitter_retries():
+    """InducingPointBasis factorises k(Z, Z) as gpytorch.solve does: plain Cholesky, then diagonal jitter 1e-8, 1e-7, 1e-6."""
+    import warnings
+
+    from projected_langevin_sampling_b200.projected_langevin_sampling.basis.inducing_point import psd_safe_cholesky
+
+    g = torch.Generator().manual_seed(0)
+    a = torch.randn(6, 6, generator=g, dtype=torch.float64)
+    spd = a @ a.T + torch.eye(6, dtype=torch.float64)
+    assert torch.equal(psd_safe_cholesky(spd), torch.linalg.cholesky(spd))  # untouched when positive definite
+    u = torch.randn(6, 2, generator=g, dtype=torch.float64)
+    near = u @ u.T  # rank 2: numerically indefinite
+    near[0, 0] -= 1e-9
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        l = psd_safe_cholesky(near)
+    assert w and "jitter" in str(w[0].message)
+    assert (l @ l.T - near).abs().max() < 1e-5
+    with pytest.raises(torch.linalg.LinAlgError):
+        psd_safe_cholesky(-torch.eye(3, dtype=torch.float64))
+    bad = spd.clone()
+    bad[2, 1] = float("nan")  # the factorisation reads the lower triangle
+    with pytest.raises(ValueError):
+        psd_safe_cholesky(bad)
+
+
+def test_gaussian_predict_is_a_light_diagonal_normal():
+    """GaussianCost.predict: mean / variance / stddev / confidence_region as the reference's gpytorch object offers, without the
+    dense Cholesky (and without failing on a zero variance, J = 1 gives NaN variance in the reference too)."""
+    from projected_langevin_sampling_b200.projected_langevin_sampling import costs, link_functions as lf
+
+    s = torch.tensor([[1.0, 3.0, 5.0], [2.0, 2.0, 2.0]], dtype=torch.float64)
+    d = costs.GaussianCost(0.1, torch.zeros(2), lf.IdentityLinkFunction()).predict(s)
+    assert torch.equal(d.mean, torch.tensor([3.0, 2.0], dtype=torch.float64))
+    assert torch.equal(d.variance, torch.tensor([4.0, 0.0], dtype=torch.float64))
+    lo, hi = d.confidence_region()
+    assert torch.equal(lo, torch.tensor([-1.0, 2.0], dtype=torch.float64)) and torch.equal(hi, torch.tensor([7.0, 2.0], dtype=torch.float64))
+    assert torch.equal(d.covariance_matrix, torch.diag(d.variance)) and d.sample().shape == (2,)
