@@ -242,6 +242,8 @@ __device__ __forceinline__ bool decide(double* scratch, const Best& best, double
     hdr_i[5] = 1;
     hdr_i[6] = slot;
     hdr_i[7] = best.cnt;
+    hdr_i[9] += 1;
+    scratch[8] = 0.0;
   } else {
     scratch[0] = sqrt(best.val);
     hdr_i[1] = best.idx;

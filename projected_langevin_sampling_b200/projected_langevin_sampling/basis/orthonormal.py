@@ -168,18 +168,23 @@ class OrthonormalBasis(PLSBasis):
             p.shape[0] == self.approximation_dimension
         ), f"Particles have shape {p.shape} but requires ({self.approximation_dimension}, J) dimension."
         eng = self.engine(p.shape[1])
-        # The gradient launches are asynchronous: enqueue them FIRST, then draw the reference's noise on the host generator
-        # (~40 ms for 1024 x 4096 normals) while the GPU works, then upload it and enqueue the update.
-        eng.gradient(p, cost.native(), cost.y_device(p.device))
-        if philox is not None:
-            mode, xi = nat.NOISE_PHILOX, None
-            seed, step_index, j_off = philox
-        else:
-            mode, xi = self._noise(p, noise)
-            seed = step_index = j_off = 0
         out = p if in_place else torch.empty_like(p, memory_format=torch.contiguous_format)
-        return eng.apply_update(p, float(step_size), out, mode, xi=xi, seed=seed, step_index=step_index, j_global_offset=j_off,
-                                in_place=in_place)
+        if philox is not None or noise is not None:
+            # the noise needs no host work: the whole step is ONE library call (pls_step_f64; pls_grad_f64 + the group
+            # all-reduce + pls_project_update_f64 when the training rows are sharded)
+            if philox is not None:
+                mode, xi = nat.NOISE_PHILOX, None
+                seed, step_index, j_off = philox
+            else:
+                mode, xi = self._noise(p, noise)
+                seed = step_index = j_off = 0
+            return eng.step(p, float(step_size), cost.native(), cost.y_device(p.device), out, mode, xi=xi, seed=seed,
+                            step_index=step_index, j_global_offset=j_off, in_place=in_place)
+        # The reference's noise is a host draw (~40 ms for 1024 x 4096 normals).  The gradient launches are asynchronous: enqueue
+        # them FIRST, draw on the host generator while the GPU works, then upload the draw and enqueue the update.
+        eng.gradient(p, cost.native(), cost.y_device(p.device))
+        mode, xi = self._noise(p, None)
+        return eng.apply_update(p, float(step_size), out, mode, xi=xi, in_place=in_place)
 
     # ---- prediction side (reference: orthonormal.py:161-244) -------------------------------------------------------------
     def sample_predictive_noise(self, particles: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
