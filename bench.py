@@ -6,19 +6,25 @@
 
 A "step" is one Langevin step over all J particles of the workload:
   C4 (default, the configuration the metric is quoted on): N=1,000,000 D=8 ARD, M=1024, J=4096, Gaussian cost.
-At --gpus N the particles are sharded (weak scaling: every GPU advances its own J particles against replicated
-X, y, Z, V~, lambda; no per-step communication; Philox noise keyed on the global particle index).
+At --gpus N the NAMED shape is strong-scaled: the J = 4096 particles are split over the N GPUs (1 x N grid, J_local = J / N,
+replicated X, y, Z, V~, lambda; no per-step communication; Philox noise keyed on the global particle index), `scaling` is
+"strong" and `config.J_global` stays 4096.  `--grid RxC` shards the training rows R ways as well (NCCL all-reduce of the
+M x J_local gradient per step over the row group).
 
 The JSON line carries: value (device-timed, inputs resident in HBM), e2e (through the reference-facing API with pinned
-HOST buffers, copies inside the timed region), roofline (FP64 tensor, live CUDA-event kernel timing), cpu_baseline
-(the oracle's reference-style torch-CPU step on the box's host cores, bounded sample), clocks, gpu_launches.
-Every timed number above is the DEFAULT path (Gram tiles regenerated inside the kernels, nothing N x M in memory, --gram generated).
-At N = 1 the line also carries informational measurements taken after and outside the timed region: library_bar (the
-reference's algebra on cuBLAS on this GPU), gram_cached / gram_staged (the same steps with the two opt-in Gram modes) and
-gaussian_normal_equations (the opt-in M x M re-association for the Gaussian cost).
+HOST buffers, copies inside the timed region), roofline (FP64 tensor, live CUDA-event timing of every contraction launch:
+pls_profile_begin / pls_profile_end), cpu_baseline (the reference's own step on the box's host cores, N = 1 only), clocks,
+gpu_launches.  Every timed number above is the DEFAULT path (Gram tiles regenerated inside the kernels, nothing N x M in memory).
+Informational objects, measured after and outside the headline's timed region:
+  N = 1: library_bar (the reference's algebra on cuBLAS on this GPU), gram_cached / gram_staged (the two opt-in Gram modes),
+         gaussian_normal_equations (opt-in M x M re-association), c2 / c3 (BASELINE configs 2 and 3: Bernoulli and Poisson costs);
+  N > 1: weak (every GPU advancing its own J = 4096 particles: last round's default), row_sharded (the same shape on a
+         2 x N/2 grid: rows sharded, NCCL gradient all-reduce timed with CUDA events), row_sharded_parity (a C5-shaped slice,
+         M = 4096, D = 16: sharded vs single-GPU particles, max relative error) and, at N = 8, c5 (BASELINE config 5 on a 2 x 4 grid).
 
-`--impl reference` times the reference's own CPU formulation of the path (the oracle port -- the reference itself needs
-gpytorch, which is not installed) on all host threads and prints the same line shape with "impl": "reference".
+`--impl reference` times the reference's own CPU implementation of the path on all host threads: the UNMODIFIED reference
+(installed under oracle/_ref by oracle/install_reference.py, run behind oracle/gpytorch_stub because gpytorch is absent) when
+it is there, else the oracle's port of it; full N and M, J_c = 256 particles per timed call (oracle/reference_arm.py).
 """
 from __future__ import annotations
 
@@ -35,6 +41,10 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+if "reference" in sys.argv and any(a.startswith("--impl") for a in sys.argv):
+    # the CPU arm: the reference moves its Gram to the GPU whenever torch.cuda.is_available() (orthonormal.py:43-45,
+    # samplers.py:36-40) -- hide the devices before torch initialises CUDA
+    os.environ["CUDA_VISIBLE_DEVICES"] = ""
 
 import torch  # noqa: E402
 
@@ -73,13 +83,14 @@ def synth(workload: dict, seed: int = 0):
     return x, y, x[z_idx].clone(), ls, outputscale
 
 
-def make_pls(workload: dict, x, y, z, ls, outputscale, gradient_reduce=None, gram_cache="auto"):
+def make_pls(workload: dict, x, y, z, ls, outputscale, gradient_reduce=None, gram_cache="auto", **basis_kw):
     import projected_langevin_sampling_b200 as pkg
     from projected_langevin_sampling_b200.projected_langevin_sampling import costs, link_functions as lf
 
     kernel = pkg.ScaleKernel(pkg.RBFKernel(ard_num_dims=x.shape[1], lengthscale=ls), outputscale=outputscale)
-    basis = pkg.OrthonormalBasis(pkg.PLSKernel(kernel, z), z, x, eigenvalue_threshold=workload.get("threshold", 0.0), verbose=False,
-                                 gradient_reduce=gradient_reduce, gram_cache=gram_cache)
+    threshold = basis_kw.pop("eigenvalue_threshold", workload.get("threshold", 0.0))
+    basis = pkg.OrthonormalBasis(pkg.PLSKernel(kernel, z), z, x, eigenvalue_threshold=threshold, verbose=False,
+                                 gradient_reduce=gradient_reduce, gram_cache=gram_cache, **basis_kw)
     if workload["cost"] == "gaussian":
         cost = costs.GaussianCost(observation_noise=0.01, y_train=y, link_function=lf.IdentityLinkFunction())
     elif workload["cost"] == "bernoulli":
@@ -142,74 +153,60 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-# ---- CPU baseline (oracle port of the reference's CPU path) -----------------------------------------------------------
-def cpu_reference_sample(workload: dict, steps: int, warmup: int):
-    """The reference-style torch-CPU Langevin step (oracle.pls_oracle.reference_style_cpu_step: left-to-right dense
-    matmuls with the N x M Gram cached, eigh(eye) + torch.normal per step) on a bounded sample: a 1/20 row slice at full
-    M with J_c = 256 particles.  The J-independent products (k(X,Z) V~ and V~^T k(Z,X), which the reference re-forms
-    every step) and the J-dependent rest are timed separately and scaled linearly to the full N and J."""
-    from oracle.pls_oracle import OrthonormalBasisOracle, RBFScaleKernel, langevin_noise
+# ---- CPU arm (the reference's own step on the host cores; oracle/reference_arm.py) ---------------------------------------------------
+def step_size_of(workload: dict) -> float:
+    # SURVEY.md section 8(d) writes eta = 1e-6 for C4; with lambda_min = 3.6e-9 the prior term eta / lambda makes that diverge within a
+    # few steps, so the bench uses 1e-9 there (the step's cost does not depend on eta) and says so in `config`
+    return 1e-9 if workload["cost"] == "gaussian" else 1e-6
 
-    torch.set_num_threads(os.cpu_count() or 1)
-    torch.set_default_dtype(torch.float64)
-    x, y, z, ls, outputscale = synth(workload)
-    n_full, j_full = workload["n"], workload["j"]
-    n_s = max(min(n_full, 1000), n_full // 20)
-    j_c = min(256, j_full)
-    xs, ys = x[:n_s], y[:n_s]
-    basis = OrthonormalBasisOracle(RBFScaleKernel(ls, outputscale), z, xs)
-    k_zx, vt, lam = basis.k_zx.contiguous(), basis.scaled_eigenvectors, basis.eigenvalues
-    p = torch.randn(vt.shape[1], j_c, generator=torch.Generator().manual_seed(1))
-    eta = 1e-9
-    t_fixed, t_rest = [], []
-    for it in range(warmup + steps):
-        t0 = time.perf_counter()
-        phi = k_zx.T @ vt  # (N_s, M_k): re-formed by the reference every step (orthonormal.py:106-108)
-        back = (-eta * vt.T) @ k_zx  # (M_k, N_s): likewise (orthonormal.py:151-154)
-        t1 = time.perf_counter()
-        f = phi @ p
-        if workload["cost"] == "gaussian":
-            dc = (1 / 0.01) * (f - ys[:, None])
-        elif workload["cost"] == "bernoulli":
-            pr = torch.clip(torch.reciprocal(1 + torch.exp(-f)), 1e-10, 1 - 1e-10)
-            dc = -ys[:, None] * (1 - pr) + (1 - ys[:, None]) * pr
-        else:
-            dc = -2 * ys[:, None] / f + 2 * f
-        xi = langevin_noise(p.shape[0], j_c)  # eigh(eye(M_k)) + torch.normal, as samplers.py:27-35
-        delta = back @ dc - eta * torch.diag(torch.reciprocal(lam)) @ p + math.sqrt(2 * eta) * xi
-        p = p + delta
-        t2 = time.perf_counter()
-        if it >= warmup:
-            t_fixed.append(t1 - t0)
-            t_rest.append(t2 - t1)
-    scale_n = n_full / n_s
-    tf, tr = statistics.median(t_fixed), statistics.median(t_rest)
-    t_step_full = scale_n * (tf + tr * (j_full / j_c))
-    return {
-        "value": j_full / t_step_full,
-        "unit": UNIT,
-        "cores": torch.get_num_threads(),
-        "kind": "port",
-        "sample": (f"oracle port of the reference torch-CPU step, dense Gram cached, rows {n_s}/{n_full} at full M={workload['m']}, "
-                   f"J_c={j_c}: J-independent products {tf:.3f}s + J-dependent {tr:.3f}s per sampled step, scaled linearly to "
-                   f"N={n_full}, J={j_full} ({steps} timed steps, median)"),
-        "sample_seconds": sum(t_fixed) + sum(t_rest),
-        "ms_per_step_extrapolated": t_step_full * 1e3,
-    }
+
+def base_config(workload: dict, world: int, grid: str) -> dict:
+    """The part of `config` that both arms print verbatim (the CPU arm runs the same workload on one host)."""
+    return {"workload": workload["label"], "N": workload["n"], "D": workload["d"], "M": workload["m"], "J_global": workload["j"],
+            "cost": workload["cost"], "step_size": step_size_of(workload), "grid": grid, "n_gpus": world,
+            "l2": "per-step working set (the Dc chunk, up to 8 GiB written + read) exceeds the 126 MB L2; no flush needed"}
+
+
+def cpu_arm(workload: dict, steps: int, warmup: int) -> dict:
+    from oracle import reference_arm
+
+    return reference_arm.run(workload, synth(workload), steps=steps, warmup=warmup, eta=step_size_of(workload))
+
+
+def cpu_arm_subprocess(workload_name: str, steps: int, warmup: int, timeout_s: int = 600):
+    """cpu_baseline of the GPU arm's line: the CPU arm in its OWN process with the GPUs hidden (the reference moves its Gram to
+    the GPU whenever torch.cuda.is_available()), on a bounded number of calls."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", workload_name, "--steps", str(steps),
+           "--warmup", str(warmup)]
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout_s, env=env)
+        line = json.loads(r.stdout.strip().splitlines()[-1])
+        return line["cpu_baseline"]
+    except Exception as exc:  # a reported baseline, never a reason to lose the line
+        return {"unavailable": f"{type(exc).__name__}: {exc}"[:300]}
 
 
 def run_reference_arm(args, workload):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
     t0 = time.perf_counter()
-    res = cpu_reference_sample(workload, steps=args.steps, warmup=args.warmup)
+    res = cpu_arm(workload, steps=args.steps, warmup=args.warmup)
+    cpu = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample", "measured")}
     line = {
         "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": res["ms_per_step_extrapolated"], "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload["label"], "note": "CPU arm: one host, all threads; value extrapolated from the bounded sample"},
-        "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "warmup": args.warmup, "ms_per_step": res["ms_per_step_whole_j_composed"], "higher_is_better": True,
+        "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": base_config(workload, world, args.grid or f"1x{world}"),
+        "note": ("CPU arm: one host, all threads, no GPU.  Each of the `steps` timed steps is ONE call of the reference's "
+                 "PLS.calculate_particle_update at full N and M on J_c = 256 particles (`cpu_baseline.measured.ms_per_call_median`); "
+                 "`ms_per_step` / `value` are the whole-J step composed from the measured J-independent and J-linear parts, with the "
+                 "J-independent work counted once (see cpu_baseline.sample)"),
+        "cpu_baseline": cpu,
         "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": time.perf_counter() - t0,
     }
@@ -281,57 +278,53 @@ def measure_fp64_peak(n: int = 8192, reps: int = 6) -> float:
     return 2.0 * n**3 / best * 1e-9
 
 
-# ---- kernel timing hooks ----------------------------------------------------------------------------------------------------
-class KernelTimer:
-    """CUDA-event pairs around every forward / backward launch of the generated-operand GEMM (on torch's current stream,
-    which is the stream the library launches on)."""
+# ---- kernel timing -----------------------------------------------------------------------------------------------------------------
+class RoleTimer:
+    """CUDA-event pairs around every launch of the contraction kernel, taken INSIDE the library on the launching stream
+    (pls_profile_begin / pls_profile_end, include/pls_b200.h): forward / backward ms, launches and algorithmic flops."""
 
-    def __init__(self):
-        self.records = []  # (kind, flops, e0, e1)
-        self.enabled = False
+    def __init__(self, ctx):
+        self.ctx = ctx
 
-    def install(self):
-        from projected_langevin_sampling_b200 import ops
+    def begin(self):
+        self.ctx.check(self.ctx.lib.pls_profile_begin(self.ctx.handle))
 
-        timer = self
-        orig_fwd, orig_bwd = ops.forward, ops.backward
+    def end(self) -> dict:
+        import ctypes as C
 
-        def fwd(ctx, kernel_id, xa, za, d, w, j, epilogue, out, **kw):
-            if not timer.enabled:
-                return orig_fwd(ctx, kernel_id, xa, za, d, w, j, epilogue, out, **kw)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            r = orig_fwd(ctx, kernel_id, xa, za, d, w, j, epilogue, out, **kw)
-            e1.record()
-            timer.records.append(("forward", 2.0 * xa.shape[0] * za.shape[0] * j, e0, e1))
-            return r
+        out = (C.c_double * 6)()
+        self.ctx.check(self.ctx.lib.pls_profile_end(self.ctx.handle, out))
+        res = {}
+        for kind, o in (("forward", 0), ("backward", 3)):
+            ms, launches, flops = out[o], int(out[o + 1]), out[o + 2]
+            if launches:
+                res[kind] = {"launches": launches, "ms_total": ms, "tflops": flops / ms * 1e-9, "flops_per_launch": flops / launches,
+                             "ms_per_launch": ms / launches}
+        ms, fl = out[0] + out[3], out[2] + out[5]
+        res["both"] = {"launches": int(out[1] + out[4]), "ms_total": ms, "tflops": fl / ms * 1e-9 if ms > 0 else 0.0}
+        return res
 
-        def bwd(ctx, kernel_id, za, xa, d, dc, j, gp, splits, accumulate, **kw):
-            if not timer.enabled:
-                return orig_bwd(ctx, kernel_id, za, xa, d, dc, j, gp, splits, accumulate, **kw)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            r = orig_bwd(ctx, kernel_id, za, xa, d, dc, j, gp, splits, accumulate, **kw)
-            e1.record()
-            timer.records.append(("backward", 2.0 * xa.shape[0] * za.shape[0] * j, e0, e1))
-            return r
 
-        ops.forward, ops.backward = fwd, bwd
+class ReduceTimer:
+    """The gradient_reduce hook of a row-sharded run with a CUDA-event pair around every all-reduce."""
 
-    def summary(self):
-        out = {}
-        for kind in ("forward", "backward"):
-            recs = [r for r in self.records if r[0] == kind]
-            if recs:
-                ms = sum(r[2].elapsed_time(r[3]) for r in recs)
-                fl = sum(r[1] for r in recs)
-                out[kind] = {"launches": len(recs), "ms_total": ms, "tflops": fl / ms * 1e-9, "flops_per_launch": fl / len(recs),
-                             "ms_per_launch": ms / len(recs)}
-        recs = self.records
-        ms = sum(r[2].elapsed_time(r[3]) for r in recs)
-        fl = sum(r[1] for r in recs)
-        out["both"] = {"launches": len(recs), "ms_total": ms, "tflops": fl / ms * 1e-9 if ms > 0 else 0.0}
-        return out
+    def __init__(self, hook):
+        self.hook, self.enabled, self.events, self.bytes = hook, False, [], 0
+
+    def __call__(self, g):
+        if not self.enabled:
+            return self.hook(g)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        self.hook(g)
+        e1.record()
+        self.events.append((e0, e1))
+        self.bytes += g.numel() * g.element_size()
+
+    def summary(self, steps: int) -> dict:
+        ms = sum(a.elapsed_time(b) for a, b in self.events)
+        return {"allreduce_calls": len(self.events), "allreduce_bytes_per_step": self.bytes // max(steps, 1),
+                "allreduce_ms_per_step": ms / max(steps, 1)}
 
 
 _REAL_STDOUT = None
@@ -353,6 +346,183 @@ def emit(line: dict):
     out.flush()
 
 
+class Runner:
+    """One process = one GPU.  Builds a (row shards x particle shards) placement of a workload and times Langevin steps on it."""
+
+    def __init__(self, args):
+        self.args = args
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local_rank)
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist_mod
+
+            self.dist = dist_mod
+            self.dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+        from projected_langevin_sampling_b200 import _native
+
+        self.ctx = _native.context()
+        self.prof = RoleTimer(self.ctx)
+        self.seed = 2024
+        self._groups = {}
+
+    def max_over_ranks(self, v: float) -> float:
+        if self.dist is None:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def placement(self, n_groups: int, j_groups: int):
+        from projected_langevin_sampling_b200.distributed import GridPlacement, gradient_allreduce, make_row_group
+
+        grid = GridPlacement(rank=self.rank, world=self.world, n_groups=n_groups, j_groups=j_groups)
+        key = (n_groups, j_groups)
+        if key not in self._groups:  # new_group is collective: every rank creates every grid it will use, in the same order
+            self._groups[key] = make_row_group(grid) if self.world > 1 else None
+        hook = gradient_allreduce(self._groups[key])
+        return grid, (ReduceTimer(hook) if hook is not None else None)
+
+    def build(self, workload, inputs, n_groups, j_groups, gram_mode, j_total=None, local=False, **basis_kw):
+        """-> dict(pls, particles, grid, reduce, j_off, j_local, n_local).  j_total = None: the workload's J split over the
+        particle shards; otherwise every particle shard owns j_total / j_groups of j_total."""
+        x, y, z, ls, outputscale = inputs
+        if local:  # this GPU alone holds the whole problem, whatever the world size
+            from projected_langevin_sampling_b200.distributed import GridPlacement
+
+            grid, reduce = GridPlacement(rank=0, world=1, n_groups=1, j_groups=1), None
+        else:
+            grid, reduce = self.placement(n_groups, j_groups)
+        r0, r1 = grid.rows(x.shape[0])
+        j_off, j_end = grid.particles(j_total if j_total is not None else workload["j"])
+        xs, ys = (x, y) if n_groups == 1 else (x[r0:r1].contiguous(), y[r0:r1].contiguous())
+        pls = make_pls(workload, xs, ys, z, ls, outputscale, gradient_reduce=reduce, gram_cache=gram_mode, **basis_kw)
+        particles = pls.initialise_particles(j_end - j_off, seed=1000 + grid.j_index)  # a row group shares its particles
+        pls.basis.engine(j_end - j_off)  # workspaces (and the Gram cache, when used) are setup, like the reference's K_zx
+        torch.cuda.synchronize()
+        return {"pls": pls, "particles": particles, "grid": grid, "reduce": reduce, "j_off": j_off, "j_local": j_end - j_off,
+                "n_local": r1 - r0, "step_no": 0}
+
+    def steps(self, run, eta, count):
+        pls, p = run["pls"], run["particles"]
+        for _ in range(count):
+            pls.step_(p, eta, philox=(self.seed, run["step_no"], run["j_off"]))
+            run["step_no"] += 1
+
+    def timed(self, run, eta, steps, clocks=False):
+        """barrier + synchronize | exactly `steps` steps between two CUDA events | synchronize + barrier; max over ranks."""
+        sampler = ClockSampler(self.local_rank) if clocks else None
+        self.barrier()
+        if sampler:
+            sampler.start()
+        launches0 = self.ctx.launches
+        if run["reduce"] is not None:
+            run["reduce"].enabled, run["reduce"].events, run["reduce"].bytes = True, [], 0
+        self.prof.begin()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        self.steps(run, eta, steps)
+        e1.record()
+        torch.cuda.synchronize()
+        ksum = self.prof.end()
+        self.barrier()
+        if run["reduce"] is not None:
+            run["reduce"].enabled = False
+        ms_local = e0.elapsed_time(e1)
+        out = {"ms_total": self.max_over_ranks(ms_local), "ms_total_this_rank": ms_local, "kernels": ksum,
+               "launches": self.ctx.launches - launches0}
+        if sampler:
+            out["clocks"] = sampler.stop()
+        return out
+
+
+def free_run(run):
+    run["pls"].basis._engines.clear()
+    run.clear()
+    torch.cuda.empty_cache()
+
+
+def small_config_object(runner, name: str, peak: float, steps: int = 50) -> dict:
+    """BASELINE configs 2 and 3 (Bernoulli + sigmoid at N=10k, M=64, J=1024; Poisson + square at N=100k, M=256, J=4096) on
+    one GPU, default generated Gram: ms/step, particle-updates/s, contraction TFLOP/s and its fraction of the FP64 peak."""
+    workload = dict(WORKLOADS[name])
+    run = runner.build(workload, synth(workload), 1, 1, False)
+    eta = step_size_of(workload)
+    runner.steps(run, eta, 5)
+    t = runner.timed(run, eta, steps)
+    ms = t["ms_total"] / steps
+    n, m, j = workload["n"], workload["m"], workload["j"]
+    obj = {"workload": workload["label"], "cost": workload["cost"], "value": j / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps,
+           "step_tflops": 4.0 * n * m * j / (ms * 1e-3) * 1e-12, "kernel_tflops": t["kernels"]["both"]["tflops"],
+           "frac": t["kernels"]["both"]["tflops"] / peak if peak else None,
+           "per_role": {k: {"tflops": v["tflops"], "ms_per_launch": v["ms_per_launch"]} for k, v in t["kernels"].items() if k != "both"},
+           "kernel_share_of_step": t["kernels"]["both"]["ms_total"] / t["ms_total"],
+           "particles_finite": bool(torch.isfinite(run["particles"]).all()), "M_k": run["pls"].basis.approximation_dimension}
+    free_run(run)
+    return obj
+
+
+def row_sharded_parity(runner, n_groups: int, j_groups: int, steps: int = 3) -> dict:
+    """tools/check_row_sharding.py's check on a C5-SHAPED slice (D=16 ARD, M=4096, 65 536 rows, 256 particles per particle
+    shard): every rank runs the slice whole on its own GPU and as its cell of the (row x particle) grid with the NCCL gradient
+    all-reduce; the particles after `steps` steps must agree (summation order differs: round-off, not bitwise)."""
+    w = dict(WORKLOADS["c5"])
+    w["n"], w["j"] = 65536, 256 * j_groups
+    inputs = synth(w)
+    eta = 1e-7
+    full = runner.build(w, inputs, 1, 1, False, local=True, eigh_device="cuda", eigenvalue_threshold=1e-6)
+    # (a 1 x 1 "grid" of this rank alone; its particles are re-drawn below so that both runs start from the same matrix)
+    basis = full["pls"].basis
+    m_k = basis.approximation_dimension
+    p0 = torch.randn(m_k, w["j"], generator=torch.Generator().manual_seed(5), dtype=torch.float64).cuda()
+    p_full = p0.clone()
+    for s in range(steps):
+        full["pls"].step_(p_full, eta, philox=(77, s, 0))
+    eig = (basis.eigenvalues.clone(), basis.eigenvectors.clone())
+    free_run(full)
+    shard = runner.build(w, inputs, n_groups, j_groups, False, eigendecomposition=eig, eigenvalue_threshold=-1.0)
+    j0, j1 = shard["j_off"], shard["j_off"] + shard["j_local"]
+    p = p0[:, j0:j1].contiguous()
+    for s in range(steps):
+        shard["pls"].step_(p, eta, philox=(77, s, j0))
+    err = ((p - p_full[:, j0:j1]).abs().max() / p_full.abs().max()).item()
+    moved = ((p_full - p0).abs().max() / p0.abs().max()).item()
+    free_run(shard)
+    return {"max_rel_err": runner.max_over_ranks(err), "grid": f"{n_groups}x{j_groups}", "rows": w["n"], "D": w["d"], "M": w["m"], "M_k": m_k,
+            "J": w["j"], "steps": steps, "relative_change_of_the_particles_over_the_run": moved, "tolerance": 1e-10,
+            "what": "C5-shaped slice: particles of the row-sharded run (NCCL all-reduce of the gradient) vs the same slice run whole on one GPU"}
+
+
+def grid_object(runner, workload, inputs, n_groups, j_groups, steps, warmup, peak, gram_mode=False) -> dict:
+    """Informational: the workload on an (n_groups x j_groups) grid -- rows sharded, gradient all-reduced over NCCL per step."""
+    t0 = time.perf_counter()
+    run = runner.build(workload, inputs, n_groups, j_groups, gram_mode)
+    setup_s = time.perf_counter() - t0
+    eta = step_size_of(workload)
+    runner.steps(run, eta, warmup)
+    t = runner.timed(run, eta, steps)
+    ms = t["ms_total"] / steps
+    n, m, j = workload["n"], workload["m"], workload["j"]
+    obj = {"workload": workload["label"], "grid": f"{n_groups}x{j_groups}", "scaling": "strong", "value": j / (ms * 1e-3), "unit": UNIT,
+           "ms_per_step": ms, "steps": steps, "warmup": warmup, "rows_per_gpu": run["n_local"], "J_per_gpu": run["j_local"], "J_global": j,
+           "step_tflops_per_gpu": 4.0 * run["n_local"] * m * run["j_local"] / (ms * 1e-3) * 1e-12,
+           "kernel_tflops_this_gpu": t["kernels"]["both"]["tflops"], "frac": t["kernels"]["both"]["tflops"] / peak if peak else None,
+           "particles_finite": bool(torch.isfinite(run["particles"]).all()), "setup_s": setup_s}
+    if run["reduce"] is not None:
+        obj.update(run["reduce"].summary(steps))
+        obj["allreduce_share_of_step"] = obj["allreduce_ms_per_step"] / ms
+        obj["collective"] = f"ncclAllReduce(sum, f64) of the M x ld(J_local) gradient over the {n_groups} ranks of a row group, once per step"
+    free_run(run)
+    return obj
+
+
 def main():
     _claim_stdout()
     ap = argparse.ArgumentParser()
@@ -363,14 +533,14 @@ def main():
     ap.add_argument("--workload", type=str, default="c4", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the informational objects measured after the headline")
     ap.add_argument("--grid", type=str, default=None,
-                    help="RxC = row shards x particle shards of ONE problem (strong scaling; needs R*C == world). Default: every GPU "
-                         "advances its own J particles against replicated data (weak scaling in J, no communication)")
+                    help="RxC = row shards x particle shards of the ONE named problem (needs R*C == world).  Default 1xN: the J particles "
+                         "are split over the N GPUs against replicated data (strong scaling, no communication)")
     ap.add_argument("--gram", type=str, default="generated", choices=["auto", "cached", "staged", "generated"],
                     help="generated (default, the path BASELINE.json's north_star names: Gram tiles recomputed inside the kernels, "
-                         "nothing N x M in memory) or cached (opt-in: k(X, Z) kept resident in HBM and streamed -- C4: 8.2 GB per "
-                         "GPU); auto caches when it fits comfortably (engine.want_gram_cache).  At N = 1 the default run also "
-                         "reports the cached mode in the line's `gram_cached` object")
+                         "nothing N x M in memory), cached (opt-in: k(X, Z) kept resident in HBM and streamed -- C4: 8.2 GB per GPU) or "
+                         "staged (a chunk-sized buffer re-formed every step); auto caches when it fits comfortably")
     ap.add_argument("--rows", dest="n", type=int, default=None, help="override N (debugging; the line then names the reduced workload)")
     ap.add_argument("--particles", dest="j", type=int, default=None)
     args = ap.parse_args()
@@ -384,107 +554,53 @@ def main():
     if args.impl == "reference":
         run_reference_arm(args, workload)
         return
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the PLS hot path has no CPU fallback (use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist_mod
 
-        dist = dist_mod
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
-    from projected_langevin_sampling_b200 import _native
-
-    ctx = _native.context()
-    t_setup = time.perf_counter()
-    x, y, z, ls, outputscale = synth(workload)
+    runner = Runner(args)
+    world, rank, dist = runner.world, runner.rank, runner.dist
+    n_groups, j_groups = (int(v) for v in args.grid.lower().split("x")) if args.grid else (1, world)
+    grid_name = f"{n_groups}x{j_groups}"
     gram_mode = {"auto": "auto", "cached": True, "staged": "staged", "generated": False}[args.gram]
-    grid = None
-    if args.grid:
-        from projected_langevin_sampling_b200.distributed import GridPlacement, gradient_allreduce, make_row_group
-
-        n_groups, j_groups = (int(v) for v in args.grid.lower().split("x"))
-        grid = GridPlacement(rank=rank, world=world, n_groups=n_groups, j_groups=j_groups)
-        row_group = make_row_group(grid) if world > 1 else None
-        r0, r1 = grid.rows(workload["n"])
-        j_off, j_end = grid.particles(workload["j"])
-        pls = make_pls(workload, x[r0:r1].contiguous(), y[r0:r1].contiguous(), z, ls, outputscale, gradient_allreduce(row_group),
-                       gram_cache=gram_mode)
-        j_local = j_end - j_off
-        del x, y
-    else:
-        pls = make_pls(workload, x, y, z, ls, outputscale, gram_cache=gram_mode)
-        j_local = workload["j"]  # weak scaling: every GPU owns J particles
-        j_off = rank * j_local
+    t_setup = time.perf_counter()
+    inputs = synth(workload)
+    run = runner.build(workload, inputs, n_groups, j_groups, gram_mode)
+    pls, particles, j_local, j_off, n_local = run["pls"], run["particles"], run["j_local"], run["j_off"], run["n_local"]
     m_k = pls.basis.approximation_dimension
     lam_min = float(pls.basis.eigenvalues.min())
-    eta = 1e-9 if workload["cost"] == "gaussian" else 1e-6
-    particles = pls.initialise_particles(j_local, seed=1000 + (grid.j_index if grid is not None else rank))  # a row group shares its particles
-    eng0 = pls.basis.engine(j_local)  # workspaces (and the Gram cache, when used) are setup, like the reference's K_zx
+    eta = step_size_of(workload)
+    eng0 = pls.basis.engine(j_local)
     gram_note = ("re-formed every step into a chunk-sized staging buffer (%.2f GB; no N x M array)" % (eng0.kstage.numel() * 8 / 1e9)
                  if eng0.kstage is not None else
                  "generated inside the kernels from the points (no N x M array)" if eng0.gram is None else
                  f"cached in HBM ({eng0.gram.numel() * 8 / 1e9:.2f} GB, computed once at setup as the reference's K_zx is) and streamed")
-    gram_is_cached = eng0.gram is not None
-    gram_key = "_cached" if gram_is_cached else ("_staged" if eng0.kstage is not None else "")
+    gram_key = "_cached" if eng0.gram is not None else ("_staged" if eng0.kstage is not None else "")
+    chunk_rows, n_chunks, splits = eng0.chunk_rows, len(eng0.chunks), eng0.splits
     del eng0
-    torch.cuda.synchronize()
     setup_s = time.perf_counter() - t_setup
 
-    timer = KernelTimer()
-    timer.install()
-    seed = 2024
-    step_no = 0
     min_warmup = 1 if args.workload == "c5" else 3  # C5 steps take ~20 s each; its line is labelled accordingly
-    for _ in range(max(args.warmup, min_warmup)):
-        pls.step_(particles, eta, philox=(seed, step_no, j_off))
-        step_no += 1
+    warmup = max(args.warmup, min_warmup)
+    runner.steps(run, eta, warmup)
     torch.cuda.synchronize()
 
-    # ---- device-resident timed region -------------------------------------------------------------------------------------
-    sampler = ClockSampler(local_rank)
-    if dist is not None:
-        dist.barrier()
-    torch.cuda.synchronize()
-    sampler.start()
-    launches0 = ctx.launches
-    timer.enabled = True
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        pls.step_(particles, eta, philox=(seed, step_no, j_off))
-        step_no += 1
-    e1.record()
-    torch.cuda.synchronize()
-    timer.enabled = False
-    if dist is not None:
-        dist.barrier()
-    ms_total = e0.elapsed_time(e1)
-    launches = ctx.launches - launches0
-    clocks = sampler.stop()
+    # ---- device-resident timed region: exactly `steps` steps -----------------------------------------------------------------------
+    t = runner.timed(run, eta, args.steps, clocks=True)
+    ms_total, ksum, launches, clocks = t["ms_total"], t["kernels"], t["launches"], t["clocks"]
     finite = bool(torch.isfinite(particles).all())
-    if dist is not None:
-        t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
     ms_per_step = ms_total / args.steps
-    j_global = workload["j"] if grid is not None else workload["j"] * world
+    j_global = workload["j"]
     value = j_global * args.steps / (ms_total * 1e-3)
-    ksum = timer.summary()
+    headline_reduce = run["reduce"].summary(args.steps) if run["reduce"] is not None else None
 
-    # ---- end-to-end through the reference-facing API with pinned host buffers ------------------------------------------------
+    # ---- end-to-end through the reference-facing API with pinned host buffers ------------------------------------------------------
     e2e = None
     if not args.no_e2e:
         p_host = particles.cpu().pin_memory()
         d_host = torch.empty_like(p_host).pin_memory()
         torch.set_default_dtype(torch.float64)  # the reference's noise draw is in the default dtype (README.md:86-87)
         torch.manual_seed(7)
-        e2e_steps = max(1, min(args.steps, 3))
+        e2e_steps = max(1, min(args.steps, 5))
 
         def e2e_step():
             p_dev = p_host.to("cuda", non_blocking=True)  # H2D: particles
@@ -494,31 +610,21 @@ def main():
             p_host.add_(d_host)
 
         e2e_step()
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
+        runner.barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
             e2e_step()
         torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        if dist is not None:
-            t = torch.tensor([dt], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
+        dt = runner.max_over_ranks(time.perf_counter() - t0)
         torch.set_default_dtype(torch.float32)
         nbytes = m_k * j_local * 8
         e2e = {"value": j_global * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": 2 * nbytes,
                "d2h_bytes_per_step": nbytes, "steps": e2e_steps, "ms_per_step": dt / e2e_steps * 1e3,
                "what": "PLS.calculate_particle_update(particles, step_size) with particles in pinned host memory: H2D particles, "
-                       "host torch.normal noise + H2D (the reference's stream), fused step, D2H delta, host add"}
+                       "host torch.normal noise + H2D (the reference's stream), fused step, D2H delta, host add; bytes are per GPU"}
+        del p_host, d_host
 
-    if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
-        return
-
-    # ---- roofline / baselines (rank 0) -----------------------------------------------------------------------------------------
+    # ---- FP64 peak (rank 0 measures, everybody needs it for the informational objects' fractions) ------------------------------------
     peak_live = measure_fp64_peak()
     peak_file = None
     try:
@@ -526,132 +632,168 @@ def main():
     except Exception:
         pass
     peak = peak_file or peak_live
-    traffic = None
-    traffic_all = {}
+
+    # ---- informational objects, after and outside the headline's timed region ------------------------------------------------------
+    extras = {}
+    do_extras = not args.no_extras and not (args.n or args.j) and args.workload == "c4" and args.grid is None
+    if world > 1 and do_extras:
+        free_run(run)
+        x_steps = max(2, min(args.steps, 5))
+        # (1) last round's default: every GPU advances its own J = 4096 particles (weak scaling in J, no communication)
+        wk = runner.build(workload, inputs, 1, world, False, j_total=workload["j"] * world)
+        runner.steps(wk, eta, 2)
+        tw = runner.timed(wk, eta, x_steps)
+        ms_w = tw["ms_total"] / x_steps
+        extras["weak"] = {"scaling": "weak", "J_per_gpu": wk["j_local"], "J_global": workload["j"] * world, "ms_per_step": ms_w, "steps": x_steps,
+                          "value": workload["j"] * world / (ms_w * 1e-3), "unit": UNIT,
+                          "kernel_tflops_this_gpu": tw["kernels"]["both"]["tflops"], "frac": tw["kernels"]["both"]["tflops"] / peak,
+                          "what": "every GPU advances its own J = 4096 particles against replicated data (round 1's default)"}
+        free_run(wk)
+        # (2) the same named shape with the ROWS sharded 2 ways as well: NCCL all-reduce of the gradient, timed
+        if world % 2 == 0:
+            extras["row_sharded"] = grid_object(runner, workload, inputs, 2, world // 2, x_steps, 2, peak)
+            extras["row_sharded_parity"] = row_sharded_parity(runner, 2, world // 2)
+        # (3) BASELINE config 5 on the whole box
+        if world == 8:
+            del inputs
+            w5 = dict(WORKLOADS["c5"])
+            extras["c5"] = grid_object(runner, w5, synth(w5), 2, 4, 2, 1, peak)
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline / baselines (rank 0) ---------------------------------------------------------------------------------------------
+    traffic, traffic_all, traffic_src = None, {}, None
     try:
         traffic_all = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
         traffic_rec = traffic_all.get(args.workload + gram_key)
-        if traffic_rec and not (args.n or args.j):
+        if traffic_rec and not (args.n or args.j) and world == 1:
             traffic = traffic_rec["per_launch_bytes_mean"]
+            traffic_src = traffic_rec.get("source")
     except Exception:
         pass
     n, m, j = workload["n"], workload["m"], workload["j"]
     achieved = ksum["both"]["tflops"]
-    n_local = (grid.rows(n)[1] - grid.rows(n)[0]) if grid is not None else n
     roofline = {
         "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
         "traffic": traffic,
-        "traffic_note": "DRAM bytes per launch (mean of the forward and backward roles) from one ncu --set full capture of this command, "
-                        "profiles/roofline_traffic.json; the kernel is FP64-pipe bound, traffic ~= the Dc chunk written / read once (+ the chunk's "
-                        "rows of the cached Gram read once)",
+        "traffic_note": ("NOT measured in this run: DRAM bytes per launch (mean of the forward and backward roles) read from profiles/roofline_traffic.json, "
+                         "one ncu --set full capture of this command" + (f" ({traffic_src})" if traffic_src else "") + ".  The step is TWO kernels "
+                         "with an N_chunk x J round trip between them: the forward writes the cost-derivative chunk Dc to HBM once and the backward "
+                         "reads it once (8.6 GB each way per 262 144-row chunk at C4 -- ~500x SURVEY 8d's 0.15 GB/step minimum for a single-pass "
+                         "design, ~2 % of the HBM bandwidth, not the limiter: the kernels are FP64-pipe bound)"),
         "kernel": "pls::gen_gemm_kernel (forward + backward roles; FP64 DMMA.8x8x4, no tcgen05 kind exists for f64); Gram " + gram_note,
         "algorithmic_flops_per_step": 4.0 * n * m * j,
         "algorithmic_flops_per_step_this_gpu": 4.0 * n_local * m * j_local,
         "per_role": {k: ksum[k] for k in ("forward", "backward") if k in ksum},
-        "kernel_share_of_step": ksum["both"]["ms_total"] / ms_total if world == 1 else None,
+        "kernel_share_of_step_this_gpu": ksum["both"]["ms_total"] / t["ms_total_this_rank"],
         "peak_source": ("cuBLAS DGEMM via torch.matmul fp64 8192^3 measured on this pool's B200 "
                         f"(profiles/fp64_peak_r01.json sustained={peak_file}, live best-of-6 in this run={peak_live:.2f}); "
                         "MEASURED_PEAKS.json holds no FP64 figure; FP64 pipe peak from tools/fp64_microbench = 37.1 TFLOP/s"),
         "step_tflops_per_gpu": 4.0 * n_local * m * j_local / (ms_per_step * 1e-3) * 1e-12,
     }
     cpu = None
-    if not args.no_cpu_baseline:
-        r = cpu_reference_sample(workload, steps=2, warmup=1)
-        cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
-    library_bar = None
-    if world == 1 and not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
+        cpu = cpu_arm_subprocess(args.workload, steps=2, warmup=1) if not (args.n or args.j) else None
+
+    if world == 1 and do_extras and not args.no_cpu_baseline:
         try:
-            library_bar = library_bar_sample(workload, pls, eta)
+            extras["library_bar"] = library_bar_sample(workload, pls, eta)
         except torch.OutOfMemoryError as exc:  # a reported comparison, never a reason to lose the line
-            library_bar = {"unavailable": str(exc).splitlines()[0]}
-    extras = {"gram_cached": None, "gram_staged": None}
-    if world == 1 and gram_mode is False and not args.no_cpu_baseline:
-        # informational measurements, after and outside the headline's timed region: the same steps with the two opt-in Gram
-        # modes -- cached (k(X, Z) computed once and kept in HBM, as the reference keeps K_zx) and staged (k(X_c, Z) re-formed
-        # every step into one chunk-sized buffer shared by the chunk's forward and backward launches; nothing N x M kept)
+            extras["library_bar"] = {"unavailable": str(exc).splitlines()[0]}
+        # the same steps with the two opt-in Gram modes -- cached (k(X, Z) computed once and kept in HBM, as the reference keeps
+        # K_zx) and staged (k(X_c, Z) re-formed every step into one chunk-sized buffer shared by the chunk's forward and backward
+        # launches; nothing N x M kept)
         notes = {"gram_cached": "OrthonormalBasis(gram_cache=True): k(X, Z) kept resident in HBM and loaded by pls_*_cached_f64 instead of "
                                 "regenerated; opt-in because north_star specifies on-the-fly Gram tiles",
                  "gram_staged": "OrthonormalBasis(gram_cache='staged'): nothing N x M kept; every step pls_gram_fill_f64 re-forms k(X_c, Z) "
                                 "for the row chunk in flight into one chunk-sized buffer that the chunk's forward and backward launches "
-                                "stream (instead of each of their J/256 column tiles regenerating it)"}
+                                "stream (instead of each of their column tiles regenerating it)"}
+        x_steps = max(2, min(args.steps, 10))
         for key, mode in (("gram_cached", True), ("gram_staged", "staged")):
             try:
                 pls.basis._gram_cache_mode, pls.basis._gram = mode, None
                 pls.basis._engines.clear()
-                q = particles.clone()
-                for k in range(2):
-                    pls.step_(q, eta, philox=(seed, k, j_off))
-                torch.cuda.synchronize()
-                timer.records = []
-                timer.enabled = True
-                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                ev0.record()
-                for k in range(args.steps):
-                    pls.step_(q, eta, philox=(seed, 2 + k, j_off))
-                ev1.record()
-                torch.cuda.synchronize()
-                timer.enabled = False
-                ms_c = ev0.elapsed_time(ev1) / args.steps
-                ks_c = timer.summary()
+                q = {"pls": pls, "particles": particles.clone(), "reduce": None, "j_off": j_off, "step_no": 0}
+                runner.steps(q, eta, 2)
+                tq = runner.timed(q, eta, x_steps)
+                ms_c = tq["ms_total"] / x_steps
+                ks_c = tq["kernels"]
                 eng_c = pls.basis.engine(j_local)
                 buf = eng_c.gram if eng_c.gram is not None else eng_c.kstage
-                extras[key] = {"value": j_local / (ms_c * 1e-3), "unit": UNIT, "ms_per_step": ms_c, "steps": args.steps,
+                extras[key] = {"value": j_local / (ms_c * 1e-3), "unit": UNIT, "ms_per_step": ms_c, "steps": x_steps,
                                "tflops": ks_c["both"]["tflops"], "frac": ks_c["both"]["tflops"] / peak if peak else None,
                                "step_tflops": 4.0 * n * m * j_local / (ms_c * 1e-3) * 1e-12,
                                "per_role_tflops": {k: ks_c[k]["tflops"] for k in ("forward", "backward") if k in ks_c},
                                "gram_bytes": int(buf.numel() * 8) if buf is not None else 0,
                                "traffic": ((traffic_all.get(args.workload + "_cached") or {}).get("per_launch_bytes_mean")
-                                           if key == "gram_cached" and not (args.n or args.j) else None),
+                                           if key == "gram_cached" else None),
                                "what": "same launch sequence with " + notes[key]}
-                del eng_c, buf
+                del eng_c, buf, q
             except torch.OutOfMemoryError as exc:
                 extras[key] = {"unavailable": str(exc).splitlines()[0]}
             finally:
                 pls.basis._gram_cache_mode, pls.basis._gram = False, None
                 pls.basis._engines.clear()
                 torch.cuda.empty_cache()
-    shortcut = None
-    if world == 1 and workload["cost"] == "gaussian" and not args.no_cpu_baseline:
-        # informational, outside the timed region and NOT the headline: the opt-in Gaussian/identity re-association
-        # (LangevinEngine._normal_equations) that turns the step into M x M algebra after one N M^2 contraction
-        try:
-            pls.basis._gaussian_normal_equations = True
-            pls.basis._engines.clear()
-            q = particles.clone()
-            t0 = time.perf_counter()
-            pls.step_(q, eta, philox=(seed, 0, j_off))
-            torch.cuda.synchronize()
-            setup_ms = (time.perf_counter() - t0) * 1e3
-            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            ev0.record()
-            for k in range(20):
-                pls.step_(q, eta, philox=(seed, 1 + k, j_off))
-            ev1.record()
-            torch.cuda.synchronize()
-            ms = ev0.elapsed_time(ev1) / 20
-            shortcut = {"value": j_local / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "setup_ms": setup_ms,
-                        "what": "opt-in OrthonormalBasis(gaussian_normal_equations=True): k(Z,X)k(X,Z)/s and k(Z,X)y/s formed once "
-                                "(setup_ms, 2 N M^2 flops), then 2 M^2 J flops per step; same particles to round-off "
-                                "(tests/test_gpu_configs.py::test_gaussian_normal_equations_shortcut); Gaussian cost only"}
-        except torch.OutOfMemoryError as exc:
-            shortcut = {"unavailable": str(exc).splitlines()[0]}
-        finally:
-            pls.basis._gaussian_normal_equations = False
-            pls.basis._engines.clear()
+        if workload["cost"] == "gaussian":
+            # the opt-in Gaussian/identity re-association (LangevinEngine._normal_equations) that turns the step into M x M algebra
+            # after one N M^2 contraction -- NOT the headline
+            try:
+                pls.basis._gaussian_normal_equations = True
+                pls.basis._engines.clear()
+                q = particles.clone()
+                t0 = time.perf_counter()
+                pls.step_(q, eta, philox=(runner.seed, 0, j_off))
+                torch.cuda.synchronize()
+                setup_ms = (time.perf_counter() - t0) * 1e3
+                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ev0.record()
+                for k in range(20):
+                    pls.step_(q, eta, philox=(runner.seed, 1 + k, j_off))
+                ev1.record()
+                torch.cuda.synchronize()
+                ms = ev0.elapsed_time(ev1) / 20
+                extras["gaussian_normal_equations"] = {
+                    "value": j_local / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "setup_ms": setup_ms,
+                    "what": "opt-in OrthonormalBasis(gaussian_normal_equations=True): k(Z,X)k(X,Z)/s and k(Z,X)y/s formed once "
+                            "(setup_ms, 2 N M^2 flops), then 2 M^2 J flops per step; same particles to round-off "
+                            "(tests/test_gpu_configs.py::test_gaussian_normal_equations_shortcut); Gaussian cost only"}
+            except torch.OutOfMemoryError as exc:
+                extras["gaussian_normal_equations"] = {"unavailable": str(exc).splitlines()[0]}
+            finally:
+                pls.basis._gaussian_normal_equations = False
+                pls.basis._engines.clear()
+        free_run(run)
+        del pls, particles
+        # BASELINE configs 2 and 3: the non-Gaussian cost epilogues, driver-timed
+        for name in ("c2", "c3"):
+            try:
+                extras[name] = small_config_object(runner, name, peak)
+            except Exception as exc:
+                extras[name] = {"unavailable": f"{type(exc).__name__}: {exc}"[:300]}
+
+    config = base_config(workload, world, grid_name)
+    config.update({
+        "M_k": m_k, "J_per_gpu": j_local, "rows_per_gpu": n_local, "lambda_min": lam_min, "gram": gram_note,
+        "row_chunk": {"rows": chunk_rows, "chunks_per_step": n_chunks, "backward_splits": splits},
+        "noise": "Philox4x32-10 on device keyed on global (row, particle)",
+        "parallelism": ((f"grid {grid_name}: rows sharded x{n_groups} (NCCL all-reduce of the M x J_local gradient per step), " if n_groups > 1 else "")
+                        + f"particles sharded x{j_groups} (J_local = {j_local} of J = {j_global}; no per-step communication)"),
+        "step_size_note": "SURVEY 8d names eta = 1e-6 for C4; lambda_min = 3.6e-9 makes the prior term eta/lambda diverge there, so 1e-9 is used "
+                          "(the cost of a step does not depend on eta)" if workload["cost"] == "gaussian" else None,
+        "particles_finite": finite, "setup_s": setup_s})
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, min_warmup),
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if grid is not None else "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic",
-        "config": {"workload": workload["label"], "N": n, "D": workload["d"], "M": m, "M_k": m_k, "J_per_gpu": j_local,
-                   "J_global": j_global, "rows_per_gpu": n_local, "cost": workload["cost"], "step_size": eta, "lambda_min": lam_min, "gram": gram_note,
-                   "noise": "Philox4x32-10 on device keyed on global (row, particle)", "parallelism": (f"grid {args.grid}: rows sharded x{grid.n_groups} (NCCL all-reduce of the M x J_local gradient per step), "
-                                   f"particles sharded x{grid.j_groups}") if grid is not None else f"particle-sharded x{world}",
-                   "l2": "per-step working set (Dc chunk 8 GiB written+read) exceeds the 126 MB L2; no flush needed",
-                   "particles_finite": finite, "setup_s": setup_s},
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": config,
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
-        "library_bar": library_bar, "gram_cached": extras["gram_cached"], "gram_staged": extras["gram_staged"],
-        "gaussian_normal_equations": shortcut,
     }
+    if headline_reduce is not None:
+        line["allreduce"] = headline_reduce
+    line.update(extras)
     emit(line)
     if dist is not None:
         dist.destroy_process_group()

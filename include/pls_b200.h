@@ -108,6 +108,11 @@ int pls_forward_tile_rows(const pls_ctx* ctx, int64_t j);
 /* force the CTA tile shape of pls_forward_f64 / pls_backward_f64: rt = 1 (64 rows x 256 particles), 2 (128 x 128),
  * 0 = choose per launch (default).  Benchmarks and tests only; the environment variable PLS_B200_TILE_RT does the same. */
 void pls_set_tile_shape(pls_ctx* ctx, int rt);
+/* accumulator sets per CTA tile of the generated-Gram kernels: ns = 0 (default) parks a second 256-column accumulator set in
+ * tensor memory (64 x 512 tiles: every generated Gram value feeds 512 particles) whenever the particle slice is an even number
+ * of 256-column tiles; ns = 1 never does.  Results are bit-identical either way (each column is accumulated in the same
+ * order).  Benchmarks and tests only; the environment variable PLS_B200_TILE_NS does the same. */
+void pls_set_tile_sets(pls_ctx* ctx, int ns);
 
 /* ---- one-time setup ------------------------------------------------------------------------------------------ */
 /* Builds the augmented layout of a point set.  x: n x d (ldx).  inv_lengthscale, centre: HOST arrays of d doubles

@@ -1,4 +1,4 @@
-"""Minimal stand-in for gpytorch, used ONLY by tests/golden/make_golden.py to execute the unmodified reference
+"""Minimal stand-in for gpytorch, used ONLY by tests/golden/make_golden.py and the CPU reference arm of bench.py (oracle/reference_arm.py) to execute the unmodified reference
 modules in the build container (gpytorch / linear_operator are not installed and there is no network).
 
 It provides just the names the reference's hot-path modules touch: kernels.Kernel (dense evaluation instead of

@@ -93,6 +93,7 @@ int pls_ctx_create(int device, pls_ctx** out) {
   c->sm_count = prop.multiProcessorCount;
   c->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
   if (const char* env = getenv("PLS_B200_TILE_RT")) c->tile_rt = atoi(env);
+  if (const char* env = getenv("PLS_B200_TILE_NS")) c->tile_ns = atoi(env);
   *out = c;
   return 0;
 }
@@ -156,7 +157,7 @@ int pls_backward_splits(const pls_ctx* ctx, int64_t n_rows, int64_t m, int64_t j
   // stages), and among the admissible counts the one that fills whole waves best (ties: fewer splits, less Gp traffic).
   const int sms = (ctx && ctx->sm_count > 0) ? ctx->sm_count : 148;
   const int rt = pls::choose_tile_rt(ctx, j);
-  const int64_t br = pls::tile_rows(rt), bj = pls::tile_cols(rt);
+  const int64_t br = pls::tile_rows(rt), bj = pls::tile_cols(rt) * pls::choose_tile_ns(ctx, j, false);  // (the generated-Gram default)
   const int64_t tiles = ((m + br - 1) / br) * ((j + bj - 1) / bj);
   if (tiles <= 0 || n_rows <= 0) return 1;
   const int64_t chunks = (n_rows + pls::BK - 1) / pls::BK;
@@ -187,6 +188,10 @@ int pls_forward_tile_rows(const pls_ctx* ctx, int64_t j) { return pls::tile_rows
 
 void pls_set_tile_shape(pls_ctx* ctx, int rt) {
   if (ctx) ctx->tile_rt = (rt == 1 || rt == 2) ? rt : 0;
+}
+
+void pls_set_tile_sets(pls_ctx* ctx, int ns) {
+  if (ctx) ctx->tile_ns = (ns == 1) ? 1 : 0;
 }
 
 int pls_prepare_points_f64(pls_ctx* ctx, int kernel_id, const double* x, int64_t n, int d, int64_t ldx,

@@ -30,6 +30,12 @@
 //   * the loop over 8-point groups is flat and branch-free (the Gram source is a template parameter) and the Gram values of
 //     a whole 32-point stage are produced one stage ahead, in two register sets that swap roles (never copied), so ptxas
 //     interleaves the 8 independent exponent chains of the NEXT stage with the DMMAs of the current one.
+//   * NS = 2 (default whenever the particle slice is an even number of 256-column tiles): the CTA tile is 64 x 512.  The 64
+//     accumulators of the SECOND 256-column half are parked in tensor memory (tcgen05.st / tcgen05.ld, 2 x 128 columns per
+//     warp, ping-pong) and swapped with the register set once per 32-point chunk; the streamed blocks come in the order
+//     A0 B0 | B1 A1 | A2 B2 ... so a chunk costs ONE swap (137 clk, tools/tmem_swap_microbench.cu) and every generated Gram
+//     value feeds 512 columns: the exponent + exp share of the FP64 pipe halves (7.4 % -> 3.7 % at D = 8).  Each column is
+//     still accumulated over the chunks in order, so the results are bit-identical to NS = 1.
 //   * optional KSRC_CACHED variant (pls_*_cached_f64): the caller keeps k(X, Z) in HBM and the kernels LOAD their fragment
 //     values (L2::evict_last, one stage ahead) instead of generating them -- the FP64 pipe then runs nothing but the
 //     contraction.  The default path generates: nothing N x M is ever in memory.
@@ -38,6 +44,7 @@
 
 #include "pls_cost.cuh"
 #include "pls_internal.h"
+#include "pls_tmem.cuh"
 
 namespace pls {
 
@@ -197,11 +204,15 @@ __device__ __forceinline__ unsigned atom_add_shared(unsigned* addr, unsigned v) 
 // columns = inducing points; no exponent work at all on the FP64 pipe, one streaming load per value instead).
 // EPI: the forward epilogue (PLS_EPI_*), a template parameter so that every kernel carries only its own epilogue's code and
 // register budget; the backward role is instantiated with EPI = -1.
-template <int NKD, bool BACKWARD, int KSRC, int RT, int EPI>
+// NS: 256-column accumulator sets per CTA tile (1, or 2 with the second set parked in tensor memory; RT = 1 and the
+// register epilogues only).
+template <int NKD, bool BACKWARD, int KSRC, int RT, int EPI, int NS>
 __global__ void __launch_bounds__(NTHREADS, 1)
     gen_gemm_kernel(const GenGemmParams p, const __grid_constant__ CUtensorMap tm3, const __grid_constant__ CUtensorMap tm2) {
   using T = Tile<RT>;
   constexpr int NT = T::NT, BR = T::BR, BJ = T::BJ, NPR = T::NPR, STAGE_BYTES = T::STAGE_BYTES;
+  constexpr int BJT = BJ * NS;  // columns of the CTA tile
+  static_assert(NS == 1 || (NS == 2 && RT == 1 && KSRC != KSRC_CACHED), "accumulator parking: 64 x 512 tiles of generated Gram values");
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);  // the swizzle needs 1024-byte stages
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);                      // [STAGES]
@@ -215,6 +226,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
                                                                                // [NWARPS][BJ] per-warp cost sums (register epilogue)
   unsigned* tile_done = released + 4;                                          // [2] warps that published their sums, by tile parity
   volatile unsigned* combined = released + 6;                                  // tiles whose sums have been combined
+  uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(smem_raw + 96);          // NS = 2: base address of the tensor-memory allocation
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -230,7 +242,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
   //   fastest: the CTAs in flight share training rows and the whole W).  The copy pipeline runs across tile boundaries (the
   //   first stages of the next tile land during the epilogue of the current one) and nothing is re-initialised per tile.
   const int64_t n_row_tiles = (p.n_rows + BR - 1) / BR;
-  const int64_t n_col_tiles = (p.j + BJ - 1) / BJ;
+  const int64_t n_col_tiles = (p.j + BJT - 1) / BJT;
   const int64_t total_tiles = n_row_tiles * n_col_tiles * (BACKWARD ? p.splits : 1);
   const int my_tiles = BACKWARD ? 1 : (int)((total_tiles - (int64_t)blockIdx.x + gridDim.x - 1) / gridDim.x);
 
@@ -252,8 +264,9 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     if (begin > end) begin = end;
   }
   const int red_len = (int)(end - begin);
-  const int nchunks = (red_len + BK - 1) / BK;         // per tile
-  const int total_gc = my_tiles * nchunks;             // chunks this CTA streams, over all its tiles (the launcher checks the range)
+  const int nchunks = (red_len + BK - 1) / BK;         // 32-point chunks per tile
+  const int nblocks = nchunks * NS;                    // streamed blocks (pipeline stages) per tile: one per chunk and column half
+  const int total_gc = my_tiles * nblocks;             // blocks this CTA streams, over all its tiles (the launcher checks the range)
   auto tile_coords = [&](int ti, int64_t& rt, int64_t& ct) {
     if (BACKWARD) {
       rt = bw_rt;
@@ -278,24 +291,36 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     released[4] = released[5] = released[6] = 0;
     fence_mbar_init();
   }
+  if (NS == 2 && warp == 0) tmem_alloc_512(tmem_base_s);  // all 512 columns: 2 warps per lane quarter x 2 slots x 128 columns
   fence_proxy_async();  // generic-proxy zero fill ordered before the async-proxy bulk copies
+  if (NS == 2) tmem_fence_before_sync();
   __syncthreads();
+  uint32_t tslot = 0;  // this warp's two parking slots: tslot, tslot + 128 (its own 32 lanes, 256 of the 512 columns)
+  if (NS == 2) {
+    tmem_fence_after_sync();
+    tslot = *tmem_base_s + ((32u * (unsigned)(warp & 3)) << 16) + 256u * (unsigned)(warp >> 2);
+  }
 
   // One thread fills a stage: one tensor-map copy for the streamed tile (all BJ/16 column blocks; rows or columns outside
   // the matrix arrive as zeros), one bulk copy for the reduction-point rows.  The 3-D map cannot describe a partial last
   // column block, so a tile that contains one uses the 2-D map block by block.  gc = chunk index over all tiles of the CTA.
+  // NS = 2: block b of a tile is chunk b / 2, and the halves alternate A B | B A | A B ... so that a chunk boundary never
+  // needs a swap of the accumulator sets; the reduction points travel with the FIRST block of their chunk only.
   auto issue = [&](int gc) {
-    const int ti = gc / nchunks;
-    const int c = gc - ti * nchunks;
+    const int ti = gc / nblocks;
+    const int b = gc - ti * nblocks;
+    const int c = (NS == 2) ? (b >> 1) : b;
+    const int half = (NS == 2) ? (((c & 1) != 0) != ((b & 1) != 0) ? 1 : 0) : 0;
+    const bool with_points = KSRC != KSRC_CACHED && (NS == 1 || (b & 1) == 0);
     int64_t rt, ct;
     tile_coords(ti, rt, ct);
-    const int64_t j0 = ct * BJ;
+    const int64_t j0 = ct * BJT + half * BJ;
     const bool use3d = p.tma3d && (j0 + BJ <= p.full_blocks * 16 || p.full_blocks * 16 == p.ldb);
     const int stage = gc % STAGES;
     const int64_t k0 = begin + (int64_t)c * BK;
     const int kc = (int)((end - k0 < BK) ? (end - k0) : BK);
     uint64_t* bar = &full[stage];
-    mbar_expect_tx(bar, (uint32_t)(STAGE_BYTES + kc * sp * 8));
+    mbar_expect_tx(bar, (uint32_t)(STAGE_BYTES + (with_points ? kc * sp * 8 : 0)));
     unsigned char* dst = sB + stage * STAGE_BYTES;
     if (use3d) {
       tma_load_3d(dst, &tm3, 0, (int)k0, (int)(j0 >> 4), bar);
@@ -303,7 +328,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 #pragma unroll 1
       for (int blk = 0; blk < NPR; ++blk) tma_load_2d(dst + blk * BLOCK_BYTES, &tm2, (int)j0 + 16 * blk, (int)k0, bar);
     }
-    if (KSRC != KSRC_CACHED) bulk_g2s(sP + stage * BK * sp, p.red_aug + k0 * sp, (uint32_t)(kc * sp * 8), bar);  // (sp = 0 when cached)
+    if (with_points) bulk_g2s(sP + stage * BK * sp, p.red_aug + k0 * sp, (uint32_t)(kc * sp * 8), bar);  // (sp = 0 when cached)
   };
   if (tid == 0) {
     for (int gc = 0; gc < STAGES && gc < total_gc; ++gc) issue(gc);
@@ -428,13 +453,14 @@ __global__ void __launch_bounds__(NTHREADS, 1)
   // tile i + 1 before the slowest warp has finished tile i -- the copy pipeline bounds the drift to STAGES stages): every
   // warp reduces its 8 rows per column with a shuffle reduce-scatter, publishes 256 sums, and the LAST warp of the tile adds
   // the 8 partials in warp order (fixed order: deterministic) and writes the row tile's sums.  No block barrier.
-  const bool sums_direct = !BACKWARD && p.wbuf_ok && nchunks > STAGES &&
+  const bool sums_direct = !BACKWARD && p.wbuf_ok && nblocks > STAGES &&
                            (EPI == PLS_EPI_COST || EPI == PLS_EPI_COST_DERIVATIVE_AND_COST);
   const bool store_direct = deriv_direct || (sums_direct && EPI == PLS_EPI_COST_DERIVATIVE_AND_COST);
   const bool gauss_store = store_direct && gauss_cost;
   const bool direct = !BACKWARD && (EPI == PLS_EPI_PREDICTION || deriv_direct || sums_direct);
-  const double inv_noise = gauss_cost ? (1.0 / p.cost.observation_noise) : 1.0;  // as cost_derivative(): gaussian.py:75-88
-  const double half_inv_noise = gauss_cost ? (1.0 / (2.0 * p.cost.observation_noise)) : 1.0;  // as cost_value(): gaussian.py:54-73
+  // (NS = 2 is short of registers in the main loop: it forms these constants, the store policy and the targets in the epilogue)
+  const double inv_noise_pre = (NS == 1 && gauss_cost) ? (1.0 / p.cost.observation_noise) : 1.0;  // as cost_derivative(): gaussian.py:75-88
+  const double half_inv_noise_pre = (NS == 1 && gauss_cost) ? (1.0 / (2.0 * p.cost.observation_noise)) : 1.0;  // as cost_value(): gaussian.py:54-73
   const bool wide_store = ((p.ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 31u) == 0);
 
   int stage = 0;
@@ -451,14 +477,13 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     int64_t rt, ct;
     tile_coords(ti, rt, ct);
     const int64_t row0 = rt * BR;
-    const int64_t j0 = ct * BJ;
     double* sY = sYall + (ti & 1) * 128;
     if (!BACKWARD && !direct && tid < BR) sY[tid] = (row0 + tid < p.n_rows) ? p.y[row0 + tid] : 0.0;
     double yreg[RT];  // direct Gaussian epilogue: the targets of this thread's rows (requested now, used after the main loop)
 #pragma unroll
     for (int h = 0; h < RT; ++h) {
       const int64_t r = row0 + (warp * RT + h) * 8 + g;
-      yreg[h] = (!BACKWARD && direct && EPI != PLS_EPI_PREDICTION && r < p.n_rows) ? p.y[r] : 0.0;
+      yreg[h] = (NS == 1 && !BACKWARD && direct && EPI != PLS_EPI_PREDICTION && r < p.n_rows) ? p.y[r] : 0.0;
     }
 #pragma unroll
     for (int h = 0; h < RT; ++h)
@@ -525,14 +550,74 @@ __global__ void __launch_bounds__(NTHREADS, 1)
       phase = nphase;
       ++gc;
     };
+    // NS = 2: one chunk = TWO streamed blocks (the two 256-column halves) sharing the chunk's Gram values k0.  The first block
+    // continues the half whose accumulators are in registers; the sets then swap through tensor memory and the second block
+    // runs the other half, so consecutive chunks visit the halves as A B | B A | A B ...  The NEXT chunk's Gram values (k1) are
+    // formed during the second block, from the points that arrived with the next chunk's first block.
+    auto dmma_block = [&](const double (&k)[LA][2][RT]) {
+      const unsigned char* bchunk = sB + stage * STAGE_BYTES;
+#pragma unroll
+      for (int q = 0; q < LA; ++q) {
+        const unsigned char* bgrp = bchunk + q * 1024;
+        mma_step(bgrp + off0, k[q][0]);
+        mma_step(bgrp + off1, k[q][1]);
+      }
+    };
+    auto release_block = [&]() {  // as in run_chunk: the last warp to release a stage refills it (no deferral: register epilogues only)
+      __syncwarp();
+      if (lane == 0) {
+        if (atom_add_shared(&released[stage], 1u) == NWARPS - 1) {
+          released[stage] = 0;
+          if (gc + STAGES < total_gc) issue(gc + STAGES);
+        }
+      }
+      stage = (stage + 1 == STAGES) ? 0 : stage + 1;
+      if (stage == 0) phase ^= 1u;
+      ++gc;
+    };
+    auto run_pair = [&](int c, double (&k0)[LA][2][RT], double (&k1)[LA][2][RT]) {
+      dmma_block(k0);  // this block's barrier was waited on when k0 was formed (its points travel with it)
+      release_block();
+      // park the finished half's accumulators, fetch the other half's (zero before its first block)
+      if constexpr (NS == 2) {
+        tmem_store64(tslot + (unsigned)(c & 1) * 128u, acc[0]);
+        tmem_wait_st();
+        if (c == 0) {
+#pragma unroll
+          for (int nt = 0; nt < NT; ++nt) {
+            acc[0][nt][0] = 0.0;
+            acc[0][nt][1] = 0.0;
+          }
+        } else {
+          tmem_load64(tslot + (unsigned)((c & 1) ^ 1) * 128u, acc[0]);
+        }
+      }
+      mbar_wait(&full[stage], phase);
+      if (c + 1 < nchunks) {
+        const int nstage = (stage + 1 == STAGES) ? 0 : stage + 1;
+        const uint32_t nphase = (nstage == 0) ? (phase ^ 1u) : phase;
+        mbar_wait(&full[nstage], nphase);
+        gram_block(sP + nstage * BK * sp, 0, (c + 1) * BK + 2 * t, k1);
+      }
+      dmma_block(k0);
+      release_block();
+    };
 #pragma unroll 1
     for (int c = 0; c < nchunks;) {
-      run_chunk(c, kA, kB);
-      ++c;
-      if (NBLK & 1) {  // the successor block sits in kB: run the next chunk with the sets swapped
-        if (c >= nchunks) break;
-        run_chunk(c, kB, kA);
+      if constexpr (NS == 2) {
+        run_pair(c, kA, kB);
         ++c;
+        if (c >= nchunks) break;
+        run_pair(c, kB, kA);
+        ++c;
+      } else {
+        run_chunk(c, kA, kB);
+        ++c;
+        if (NBLK & 1) {  // the successor block sits in kB: run the next chunk with the sets swapped
+          if (c >= nchunks) break;
+          run_chunk(c, kB, kA);
+          ++c;
+        }
       }
     }
     const int estage = (stage == 0) ? STAGES - 1 : stage - 1;  // the stage of the tile's last chunk
@@ -540,6 +625,18 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     // ---- epilogue ---------------------------------------------------------------------------------------------------
     // Column map: thread (g,t) holds, for column pair pr, the 4 consecutive columns j0 + 16 pr + 4 t + {0,1,2,3} as
     // acc[h][2pr][0], acc[h][2pr+1][0], acc[h][2pr][1], acc[h][2pr+1][1]; rows row0 + 8 (RT warp + h) + g.
+    // NS = 2: the epilogue runs once per 256-column half -- first the half whose accumulators are in registers after the last
+    // chunk, then the parked one.  vt numbers the halves of this CTA's tiles (the cost-sum hand-over below counts in them).
+#pragma unroll 1
+    for (int eh = 0; eh < NS; ++eh) {
+    int half = 0;
+    if constexpr (NS == 2) {
+      const int hreg = ((nchunks - 1) & 1) ? 0 : 1;
+      half = (eh == 0) ? hreg : 1 - hreg;
+      if (eh == 1 && nchunks > 0) tmem_load64(tslot + (unsigned)((nchunks - 1) & 1) * 128u, acc[0]);
+    }
+    const int64_t j0 = ct * BJT + half * BJ;
+    const int vt = ti * NS + eh;
     if (BACKWARD) {
 #pragma unroll
       for (int h = 0; h < RT; ++h) {
@@ -568,13 +665,23 @@ __global__ void __launch_bounds__(NTHREADS, 1)
           }
         }
       }
-      return;
+      continue;
     }
 
     if (direct) {
       const int64_t cols_here = (p.j - j0 < BJ) ? (p.j - j0) : BJ;
+      const double inv_noise = (NS == 2 && gauss_cost) ? (1.0 / p.cost.observation_noise) : inv_noise_pre;
+      const double half_inv_noise = (NS == 2 && gauss_cost) ? (1.0 / (2.0 * p.cost.observation_noise)) : half_inv_noise_pre;
+      const uint64_t pol_store = (NS == 2) ? l2_policy_evict_first() : pol_stream;
+      if (NS == 2 && eh == 0 && EPI != PLS_EPI_PREDICTION) {
+#pragma unroll
+        for (int h = 0; h < RT; ++h) {
+          const int64_t r = row0 + (warp * RT + h) * 8 + g;
+          yreg[h] = (r < p.n_rows) ? p.y[r] : 0.0;
+        }
+      }
       if (sums_direct) {  // the per-warp buffer is single: the previous tile's sums must have been combined (never spins)
-        while (*combined < (unsigned)ti) {
+        while (*combined < (unsigned)vt) {
         }
       }
 #pragma unroll
@@ -617,7 +724,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
           if (col + 3 < cols_here) {
             if (wide_store) {
               asm volatile("st.global.L2::cache_hint.v4.f64 [%0], {%1,%2,%3,%4}, %5;" ::"l"(orow + col), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]),
-                           "l"(pol_stream)
+                           "l"(pol_store)
                            : "memory");
             } else {
               double2* dst = reinterpret_cast<double2*>(orow + col);
@@ -646,7 +753,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
       if (sums_direct) {
         __syncwarp();
         unsigned last = 0;
-        if (lane == 0) last = (atom_add_acq_rel_shared(&tile_done[ti & 1], 1u) == NWARPS - 1) ? 1u : 0u;
+        if (lane == 0) last = (atom_add_acq_rel_shared(&tile_done[vt & 1], 1u) == NWARPS - 1) ? 1u : 0u;
         last = __shfl_sync(0xffffffffu, last, 0);
         if (last) {  // every warp has published this tile's sums: add the partials in warp order
           double* orow = ((EPI == PLS_EPI_COST) ? p.out + rt * p.ldo : p.out2 + rt * p.ldo2) + j0;
@@ -658,13 +765,13 @@ __global__ void __launch_bounds__(NTHREADS, 1)
           }
           __syncwarp();
           if (lane == 0) {
-            tile_done[ti & 1] = 0;
+            tile_done[vt & 1] = 0;
             __threadfence_block();
-            *combined = (unsigned)(ti + 1);
+            *combined = (unsigned)(vt + 1);
           }
         }
       }
-      if (ti + 1 < my_tiles) {
+      if (eh == NS - 1 && ti + 1 < my_tiles) {
         int64_t rtn, ctn;
         tile_coords(ti + 1, rtn, ctn);
         load_rows(rtn * BR, a2, crow);
@@ -755,20 +862,26 @@ __global__ void __launch_bounds__(NTHREADS, 1)
       issue(gc - 1 + STAGES);  // the refill deferred at the tile's last chunk
     }
     if (ti + 1 < my_tiles) load_rows(next_row0, a2, crow);
+    }  // halves
+  }
+  if (NS == 2) {  // every warp has drained its parking slots: release the tensor memory
+    tmem_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc_512(*tmem_base_s);
   }
 }
 
-template <int NKD, bool BACKWARD, int KSRC, int RT, int EPI>
+template <int NKD, bool BACKWARD, int KSRC, int RT, int EPI, int NS = 1>
 cudaError_t launch_one(const pls_ctx* ctx, GenGemmParams p, cudaStream_t stream) {
   using T = Tile<RT>;
   if (KSRC == KSRC_CACHED) p.sp = 0;  // no point rows are staged
-  int64_t grid = ((p.n_rows + T::BR - 1) / T::BR) * ((p.j + T::BJ - 1) / T::BJ);
+  int64_t grid = ((p.n_rows + T::BR - 1) / T::BR) * ((p.j + T::BJ * NS - 1) / (T::BJ * NS));
   if (BACKWARD) grid *= p.splits;
   else {
     const int64_t tiles = grid;
     if (grid > ctx->sm_count) grid = ctx->sm_count;  // persistent forward: one CTA per SM walks the tiles
     // the kernel counts the chunks a CTA streams over all its tiles in 32 bits
-    if (grid > 0 && ((tiles + grid - 1) / grid) * ((p.red_total + BK - 1) / BK) > 2147483647LL) return cudaErrorInvalidConfiguration;
+    if (grid > 0 && ((tiles + grid - 1) / grid) * ((p.red_total + BK - 1) / BK) * NS > 2147483647LL) return cudaErrorInvalidConfiguration;
   }
   if (grid <= 0 || p.red_total <= 0) return cudaSuccess;
   if (grid > 2147483647LL) return cudaErrorInvalidConfiguration;
@@ -783,9 +896,9 @@ cudaError_t launch_one(const pls_ctx* ctx, GenGemmParams p, cudaStream_t stream)
   cudaError_t e = make_stream_maps(ctx, p.b, p.red_total, p.ldb, T::NPR, &tm3, &tm2, &p.tma3d);
   if (e != cudaSuccess) return e;
   p.full_blocks = p.ldb / 16;
-  e = cudaFuncSetAttribute(gen_gemm_kernel<NKD, BACKWARD, KSRC, RT, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  e = cudaFuncSetAttribute(gen_gemm_kernel<NKD, BACKWARD, KSRC, RT, EPI, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  gen_gemm_kernel<NKD, BACKWARD, KSRC, RT, EPI><<<(unsigned)grid, NTHREADS, smem, stream>>>(p, tm3, tm2);
+  gen_gemm_kernel<NKD, BACKWARD, KSRC, RT, EPI, NS><<<(unsigned)grid, NTHREADS, smem, stream>>>(p, tm3, tm2);
   return cudaGetLastError();
 }
 
@@ -801,6 +914,13 @@ cudaError_t launch_role(const pls_ctx* ctx, const GenGemmParams& p, cudaStream_t
     }
   }
   const bool rbf = (p.kernel_id == PLS_KERNEL_RBF);
+  // 64 x 512 tiles with the second accumulator set parked in tensor memory (NS = 2): RBF, an even number of 256-column tiles,
+  // and an epilogue that runs from registers (the cost-sum epilogues need room for the per-warp sums and > STAGES blocks per tile)
+  if (rbf && p.rt == 1 && choose_tile_ns(ctx, p.j, false) == 2) {
+    const bool sums = ROLE == PLS_EPI_COST || ROLE == PLS_EPI_COST_DERIVATIVE_AND_COST;
+    const bool sums_from_registers = (int64_t)gen_gemm_smem_bytes_wbuf<1>(p.sp) <= ctx->max_smem_optin && 2 * ((p.red_total + BK - 1) / BK) > STAGES;
+    if (!sums || sums_from_registers) return launch_one<NKD, BW, KSRC_RBF, 1, ROLE, 2>(ctx, p, stream);
+  }
   if (p.rt == 1) return rbf ? launch_one<NKD, BW, KSRC_RBF, 1, ROLE>(ctx, p, stream) : launch_one<NKD, BW, KSRC_LINEAR, 1, ROLE>(ctx, p, stream);
   return rbf ? launch_one<NKD, BW, KSRC_RBF, 2, ROLE>(ctx, p, stream) : launch_one<NKD, BW, KSRC_LINEAR, 2, ROLE>(ctx, p, stream);
 }

@@ -16,6 +16,7 @@ struct pls_ctx {
   int max_smem_optin = 0;
   const uint64_t* step_counter = nullptr;  // device counter added to pls_project_update_f64's `step` (pls_set_step_counter)
   int tile_rt = 0;  // 0 = choose per launch from the particle count; 1 / 2 force a tile shape (PLS_B200_TILE_RT, tests)
+  int tile_ns = 0;  // 0 = park a second accumulator set in tensor memory whenever the shape allows; 1 = never (PLS_B200_TILE_NS, tests)
   std::string error;
   // pls_profile_begin / pls_profile_end: CUDA-event pairs around every launch of the hot kernel (role 0 forward, 1 backward)
   struct ProfileRecord {
@@ -62,6 +63,13 @@ struct GenGemmParams {
 inline int choose_tile_rt(const pls_ctx* ctx, int64_t j) {
   if (ctx && (ctx->tile_rt == 1 || ctx->tile_rt == 2)) return ctx->tile_rt;
   return (j <= 128) ? 2 : 1;
+}
+
+// accumulator sets per CTA tile of the generated-Gram kernels: 2 (64 x 512 tile, the second set parked in tensor memory) when the
+// particle slice is an even number of 256-column tiles, else 1.  The cached-Gram kernels generate nothing and stay at 1.
+inline int choose_tile_ns(const pls_ctx* ctx, int64_t j, bool cached) {
+  if (cached || choose_tile_rt(ctx, j) != 1 || (ctx && ctx->tile_ns == 1)) return 1;
+  return (((j + 255) / 256) % 2 == 0) ? 2 : 1;
 }
 
 // Tensor maps of the streamed matrix b (rows x ldb doubles, 16-byte aligned, ldb even) for the hot kernel's stages of 32 rows

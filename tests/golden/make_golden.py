@@ -1,7 +1,7 @@
 """Generate golden fixtures by EXECUTING THE UNMODIFIED REFERENCE (`/root/reference`) in the build container.
 
 The reference imports gpytorch at module top level and gpytorch is not installed here, so its modules are run
-behind `tests/golden/gpytorch_stub` (dense kernel evaluation; RBF arithmetic = the oracle's restatement of the
+behind `oracle/gpytorch_stub` (dense kernel evaluation; RBF arithmetic = the oracle's restatement of the
 gpytorch formula).  Everything else -- OrthonormalBasis, the costs (incl. the autograd derivative), PLS, the
 sampler, the ConditionalVariance selector -- is the reference's own code, so these fixtures pin the parts the
 reference's unit tests leave unpinned (the Langevin update, whole trajectories, selector runs with m > 2).
@@ -15,7 +15,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
-sys.path[:0] = [os.path.join(HERE, "gpytorch_stub"), ROOT, "/root/reference"]
+sys.path[:0] = [os.path.join(ROOT, "oracle", "gpytorch_stub"), ROOT, "/root/reference"]
 
 import numpy as np  # noqa: E402
 import torch  # noqa: E402

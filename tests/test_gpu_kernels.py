@@ -384,3 +384,89 @@ def test_gram_fill_matches_gram(ctx, n, m, d):
         tol = 8 * np.finfo(np.float64).eps
         assert ((got - want).abs() <= tol * want.abs().clamp_min(1e-300) + (1e-15 if kid == nat.KERNEL_LINEAR else 0.0)).all()
         assert (buf[n:] == -7.0).all() and (buf[:, m:] == -7.0).all()
+
+
+@pytest.mark.parametrize(
+    "n,m,d,j,ld,cost_name",
+    [
+        (1000, 200, 8, 512, 512, "gaussian"),     # one 64 x 512 tile per row tile, several chunks
+        (777, 130, 3, 900, 912, "poisson"),       # 4 column blocks of 256, the last one partial (388 valid columns); ragged rows / points
+        (300, 33, 1, 1024, 1024, "bernoulli"),    # two 512-column tiles, 2 chunks (odd / even chunk counts park different halves)
+        (200, 32, 16, 512, 520, "gaussian"),      # exactly one chunk: the parked half is never reloaded inside the main loop; 2-D TMA path
+        (5000, 96, 5, 2048, 2048, "student_t"),   # persistent forward: several tiles per CTA
+    ],
+)
+def test_parked_accumulators_are_bit_identical(ctx, n, m, d, j, ld, cost_name):
+    """NS = 2 (64 x 512 CTA tiles, the second accumulator set parked in tensor memory and swapped once per chunk) accumulates every
+    column over the chunks in the same order as NS = 1, so every entry point must return the SAME BITS either way: forward
+    (prediction, cost derivative, cost sums, fused derivative + sums) and backward with several split counts."""
+    from projected_langevin_sampling_b200 import _native as nat, ops
+
+    g = torch.Generator().manual_seed(n + m + j)
+    x = torch.randn(n, d, generator=g, dtype=torch.float64).cuda()
+    z = torch.randn(m, d, generator=g, dtype=torch.float64).cuda()
+    inv_ls = [1.0 / (1.0 + 0.1 * k + d ** 0.5) for k in range(d)]
+    centre = z.mean(0).tolist()
+    xa = ops.prepare_points(ctx, nat.KERNEL_RBF, x, inv_ls, centre, 0.0)
+    za = ops.prepare_points(ctx, nat.KERNEL_RBF, z, inv_ls, centre, float(np.log(1.1)))
+    w = (0.3 * torch.randn(m, ld, generator=g, dtype=torch.float64)).cuda()
+    dc = torch.randn(n, ld, generator=g, dtype=torch.float64).cuda()
+    cost = nat.PlsCost()
+    cost.closed_form, cost.observation_noise, cost.link_jitter = 1, 0.3, 1e-10
+    cost.degrees_of_freedom, cost.scale = 4.0, 1.0
+    if cost_name == "gaussian":
+        cost.cost_id, cost.link_id = nat.COST_GAUSSIAN, nat.LINK_IDENTITY
+        y = torch.randn(n, generator=g, dtype=torch.float64).cuda()
+    elif cost_name == "poisson":
+        cost.cost_id, cost.link_id = nat.COST_POISSON, nat.LINK_SQUARE
+        y = torch.poisson(2.0 * torch.ones(n), generator=g).double().cuda()
+    elif cost_name == "bernoulli":
+        cost.cost_id, cost.link_id = nat.COST_BERNOULLI, nat.LINK_SIGMOID
+        y = torch.bernoulli(0.5 * torch.ones(n), generator=g).double().cuda()
+    else:
+        cost.cost_id, cost.link_id = nat.COST_STUDENT_T, nat.LINK_IDENTITY
+        y = torch.randn(n, generator=g, dtype=torch.float64).cuda()
+    tiles = (n + 63) // 64
+
+    def run_all():
+        out = {}
+        for name, epi in (("f", nat.EPI_PREDICTION), ("dc", nat.EPI_COST_DERIVATIVE)):
+            buf = torch.full((n, ld), 7.0, dtype=torch.float64).cuda()
+            ops.forward(ctx, nat.KERNEL_RBF, xa, za, d, w, j, epi, buf, cost=cost, y=y)
+            out[name] = buf
+        part = torch.full((tiles, ld), 7.0, dtype=torch.float64).cuda()
+        ops.forward(ctx, nat.KERNEL_RBF, xa, za, d, w, j, nat.EPI_COST, part, cost=cost, y=y)
+        out["sums"] = part
+        dc2 = torch.full((n, ld), 7.0, dtype=torch.float64).cuda()
+        part2 = torch.full((tiles, ld), 7.0, dtype=torch.float64).cuda()
+        ops.forward_step(ctx, nat.KERNEL_RBF, xa, za, d, w, j, cost, y, dc2, part2)
+        out["dc2"], out["sums2"] = dc2, part2
+        for splits in (1, 3):
+            gp = torch.full((splits, m, ld), 7.0, dtype=torch.float64).cuda()
+            ops.backward(ctx, nat.KERNEL_RBF, za, xa, d, dc, j, gp, splits, accumulate=False)
+            ops.backward(ctx, nat.KERNEL_RBF, za, xa, d, dc, j, gp, splits, accumulate=True)
+            out[f"gp{splits}"] = gp
+        torch.cuda.synchronize()
+        return out
+
+    ctx.lib.pls_set_tile_sets(ctx.handle, 1)
+    try:
+        want = run_all()
+    finally:
+        ctx.lib.pls_set_tile_sets(ctx.handle, 0)
+    got = run_all()
+    k_xz = ops.gram(ctx, nat.KERNEL_RBF, xa, za, d)
+    ref_f = k_xz @ w[:, :j]
+    assert (want["f"][:, :j] - ref_f).abs().max().item() < 1e-12 * max(1.0, ref_f.abs().max().item())
+    # with at most 3 chunks per tile the NS = 1 kernel runs the cost-sum epilogues (COST and the fused derivative + cost) through its
+    # shared-memory staged path -- another row order for the sums, IEEE division / exp instead of the branch-free routines for the
+    # derivative -- while NS = 2 streams twice as many blocks and qualifies for the register epilogue: round-off agreement only
+    staged_sums = (m + 31) // 32 <= 3
+    for name in want:
+        a, b = got[name], want[name]
+        if staged_sums and name in ("sums", "sums2", "dc2"):
+            assert (a[:, :j] - b[:, :j]).abs().max().item() <= 1e-13 * max(1.0, b[:, :j].abs().max().item())
+            continue
+        same = (a == b) | (torch.isnan(a) & torch.isnan(b))
+        assert bool(same.all()), f"{name}: {int((~same).sum())} entries differ between NS = 2 and NS = 1"
+        assert (a[..., j:] == 7.0).all(), f"{name}: wrote outside the logical matrix"
