@@ -203,14 +203,18 @@ def test_bench_reference_arm_prints_one_contract_line():
     contract's keys, whatever the libraries print."""
     import json
 
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
-                       capture_output=True, text=True, timeout=600)
+    # (a 20 000-row slice: the full-N arm needs ~30 GB of host memory and minutes of CPU time)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--rows", "20000"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
     assert len(lines) == 1, r.stdout[:500]
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["unit"] == "particle-updates/s" and d["higher_is_better"] is True
-    assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    # "reference+stub" = the unmodified reference installed under oracle/_ref (build container / GPU box), "port" = the oracle's
+    # restatement when that install is absent
+    assert d["value"] > 0 and d["cpu_baseline"]["kind"] in ("reference+stub", "port") and d["cpu_baseline"]["cores"] >= 1
+    assert d["config"]["J_global"] == 4096 and d["cpu_baseline"]["measured"]["j_chunk"] == 256
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     for key in ("metric", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "vs_baseline", "dtype", "data", "config"):
         assert key in d
