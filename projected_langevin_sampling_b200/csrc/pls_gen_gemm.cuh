@@ -118,6 +118,45 @@ static __device__ __noinline__ D4 cost_value4(const pls_cost* c, const double* e
   return f;
 }
 
+// Four cost VALUES and four DERIVATIVES per call, for the fused epilogue of pls_forward_step_f64 (the training loop's energy
+// comes from the same F tile as the gradient): one specialised body evaluates both, so whatever the two share -- the link
+// (sigmoid: one exp and one division instead of two of each), the residuals, the Student-t / mixture denominators -- is
+// computed once, and the eight dependent FP64 chains interleave instead of running as two calls of four.
+struct D8 {
+  D4 d, c;
+};
+template <int CID, int LID, int CF>
+static __device__ __forceinline__ D8 cost_both4_as(const pls_cost& c, double y, const D4& f, const double* exp_table) {
+  pls_cost cc = c;
+  cc.cost_id = CID;
+  cc.link_id = LID;
+  cc.closed_form = CF;
+  const FlatMath m{exp_table};
+  D8 r;
+  r.d.a = cost_derivative(cc, y, f.a, m);
+  r.d.b = cost_derivative(cc, y, f.b, m);
+  r.d.c = cost_derivative(cc, y, f.c, m);
+  r.d.d = cost_derivative(cc, y, f.d, m);
+  r.c.a = cost_value(cc, y, f.a, m);
+  r.c.b = cost_value(cc, y, f.b, m);
+  r.c.c = cost_value(cc, y, f.c, m);
+  r.c.d = cost_value(cc, y, f.d, m);
+  return r;
+}
+static __device__ __noinline__ D8 cost_both4(const pls_cost* c, const double* exp_table, double y, D4 f) {
+  const pls_cost cc = *c;
+#define PLS_CASE(CID, LID)                                                   \
+  case (CID * 8 + LID * 2 + 0): return cost_both4_as<CID, LID, 0>(cc, y, f, exp_table); \
+  case (CID * 8 + LID * 2 + 1): return cost_both4_as<CID, LID, 1>(cc, y, f, exp_table);
+#define PLS_CASES(CID) PLS_CASE(CID, 0) PLS_CASE(CID, 1) PLS_CASE(CID, 2) PLS_CASE(CID, 3)
+  switch (cc.cost_id * 8 + cc.link_id * 2 + (cc.closed_form != 0)) {
+    PLS_CASES(0) PLS_CASES(1) PLS_CASES(2) PLS_CASES(3) PLS_CASES(4)
+  }
+#undef PLS_CASES
+#undef PLS_CASE
+  return D8{f, f};
+}
+
 template <int RT>
 struct Tile {
   static constexpr int NT = 32 / RT;          // n8 column tiles per warp
@@ -305,20 +344,24 @@ __global__ void __launch_bounds__(NTHREADS, 1)
   // the matrix arrive as zeros), one bulk copy for the reduction-point rows.  The 3-D map cannot describe a partial last
   // column block, so a tile that contains one uses the 2-D map block by block.  gc = chunk index over all tiles of the CTA.
   // NS = 2: block b of a tile is chunk b / 2, and the halves alternate A B | B A | A B ... so that a chunk boundary never
-  // needs a swap of the accumulator sets; the reduction points travel with the FIRST block of their chunk only.
+  // needs a swap of the accumulator sets.  The Gram values of chunk c + 1 are formed during the SECOND block of chunk c, so
+  // that block carries the reduction points of chunk c + 1 (read from the stage in use, before it is released: no warp ever
+  // waits on a block ahead of the one it multiplies); the tile's first block carries the points of chunk 0 for the prologue.
   auto issue = [&](int gc) {
     const int ti = gc / nblocks;
     const int b = gc - ti * nblocks;
     const int c = (NS == 2) ? (b >> 1) : b;
     const int half = (NS == 2) ? (((c & 1) != 0) != ((b & 1) != 0) ? 1 : 0) : 0;
-    const bool with_points = KSRC != KSRC_CACHED && (NS == 1 || (b & 1) == 0);
+    const int cp = (NS == 2) ? ((b == 0) ? 0 : ((b & 1) ? c + 1 : nchunks)) : c;  // chunk whose points travel with this block
+    const bool with_points = KSRC != KSRC_CACHED && cp < nchunks;
     int64_t rt, ct;
     tile_coords(ti, rt, ct);
     const int64_t j0 = ct * BJT + half * BJ;
     const bool use3d = p.tma3d && (j0 + BJ <= p.full_blocks * 16 || p.full_blocks * 16 == p.ldb);
     const int stage = gc % STAGES;
     const int64_t k0 = begin + (int64_t)c * BK;
-    const int kc = (int)((end - k0 < BK) ? (end - k0) : BK);
+    const int64_t kp0 = begin + (int64_t)cp * BK;
+    const int kc = (int)((end - kp0 < BK) ? (end - kp0) : BK);  // points copied
     uint64_t* bar = &full[stage];
     mbar_expect_tx(bar, (uint32_t)(STAGE_BYTES + (with_points ? kc * sp * 8 : 0)));
     unsigned char* dst = sB + stage * STAGE_BYTES;
@@ -328,7 +371,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 #pragma unroll 1
       for (int blk = 0; blk < NPR; ++blk) tma_load_2d(dst + blk * BLOCK_BYTES, &tm2, (int)j0 + 16 * blk, (int)k0, bar);
     }
-    if (with_points) bulk_g2s(sP + stage * BK * sp, p.red_aug + k0 * sp, (uint32_t)(kc * sp * 8), bar);  // (sp = 0 when cached)
+    if (with_points) bulk_g2s(sP + stage * BK * sp, p.red_aug + kp0 * sp, (uint32_t)(kc * sp * 8), bar);  // (sp = 0 when cached)
   };
   if (tid == 0) {
     for (int gc = 0; gc < STAGES && gc < total_gc; ++gc) issue(gc);
@@ -458,9 +501,8 @@ __global__ void __launch_bounds__(NTHREADS, 1)
   const bool store_direct = deriv_direct || (sums_direct && EPI == PLS_EPI_COST_DERIVATIVE_AND_COST);
   const bool gauss_store = store_direct && gauss_cost;
   const bool direct = !BACKWARD && (EPI == PLS_EPI_PREDICTION || deriv_direct || sums_direct);
-  // (NS = 2 is short of registers in the main loop: it forms these constants, the store policy and the targets in the epilogue)
-  const double inv_noise_pre = (NS == 1 && gauss_cost) ? (1.0 / p.cost.observation_noise) : 1.0;  // as cost_derivative(): gaussian.py:75-88
-  const double half_inv_noise_pre = (NS == 1 && gauss_cost) ? (1.0 / (2.0 * p.cost.observation_noise)) : 1.0;  // as cost_value(): gaussian.py:54-73
+  const double inv_noise = gauss_cost ? (1.0 / p.cost.observation_noise) : 1.0;  // as cost_derivative(): gaussian.py:75-88
+  const double half_inv_noise = gauss_cost ? (1.0 / (2.0 * p.cost.observation_noise)) : 1.0;  // as cost_value(): gaussian.py:54-73
   const bool wide_store = ((p.ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 31u) == 0);
 
   int stage = 0;
@@ -483,7 +525,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 #pragma unroll
     for (int h = 0; h < RT; ++h) {
       const int64_t r = row0 + (warp * RT + h) * 8 + g;
-      yreg[h] = (NS == 1 && !BACKWARD && direct && EPI != PLS_EPI_PREDICTION && r < p.n_rows) ? p.y[r] : 0.0;
+      yreg[h] = (!BACKWARD && direct && EPI != PLS_EPI_PREDICTION && r < p.n_rows) ? p.y[r] : 0.0;
     }
 #pragma unroll
     for (int h = 0; h < RT; ++h)
@@ -576,7 +618,8 @@ __global__ void __launch_bounds__(NTHREADS, 1)
       ++gc;
     };
     auto run_pair = [&](int c, double (&k0)[LA][2][RT], double (&k1)[LA][2][RT]) {
-      dmma_block(k0);  // this block's barrier was waited on when k0 was formed (its points travel with it)
+      if (c > 0) mbar_wait(&full[stage], phase);  // (chunk 0: the tile prologue waited for this block, which carries its points)
+      dmma_block(k0);
       release_block();
       // park the finished half's accumulators, fetch the other half's (zero before its first block)
       if constexpr (NS == 2) {
@@ -593,12 +636,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
         }
       }
       mbar_wait(&full[stage], phase);
-      if (c + 1 < nchunks) {
-        const int nstage = (stage + 1 == STAGES) ? 0 : stage + 1;
-        const uint32_t nphase = (nstage == 0) ? (phase ^ 1u) : phase;
-        mbar_wait(&full[nstage], nphase);
-        gram_block(sP + nstage * BK * sp, 0, (c + 1) * BK + 2 * t, k1);
-      }
+      if (c + 1 < nchunks) gram_block(sP + stage * BK * sp, 0, (c + 1) * BK + 2 * t, k1);  // the next chunk's points came with this block
       dmma_block(k0);
       release_block();
     };
@@ -608,7 +646,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
         run_pair(c, kA, kB);
         ++c;
         if (c >= nchunks) break;
-        run_pair(c, kB, kA);
+        run_pair(c, kB, kA);  // (a single copy of the pair + 16 register moves was tried: forward 32.1 -> 29.8 TFLOP/s)
         ++c;
       } else {
         run_chunk(c, kA, kB);
@@ -670,16 +708,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 
     if (direct) {
       const int64_t cols_here = (p.j - j0 < BJ) ? (p.j - j0) : BJ;
-      const double inv_noise = (NS == 2 && gauss_cost) ? (1.0 / p.cost.observation_noise) : inv_noise_pre;
-      const double half_inv_noise = (NS == 2 && gauss_cost) ? (1.0 / (2.0 * p.cost.observation_noise)) : half_inv_noise_pre;
-      const uint64_t pol_store = (NS == 2) ? l2_policy_evict_first() : pol_stream;
-      if (NS == 2 && eh == 0 && EPI != PLS_EPI_PREDICTION) {
-#pragma unroll
-        for (int h = 0; h < RT; ++h) {
-          const int64_t r = row0 + (warp * RT + h) * 8 + g;
-          yreg[h] = (r < p.n_rows) ? p.y[r] : 0.0;
-        }
-      }
+
       if (sums_direct) {  // the per-warp buffer is single: the previous tile's sums must have been combined (never spins)
         while (*combined < (unsigned)vt) {
         }
@@ -693,7 +722,17 @@ __global__ void __launch_bounds__(NTHREADS, 1)
           const int64_t r = row0 + (warp * RT + h) * 8 + g;
           const bool rv = r < p.n_rows;
           double v[4] = {acc[h][2 * pr][0], acc[h][2 * pr + 1][0], acc[h][2 * pr][1], acc[h][2 * pr + 1][1]};
-          if (sums_direct) {
+          if (EPI == PLS_EPI_COST_DERIVATIVE_AND_COST && sums_direct && !gauss_cost) {  // both from one specialised call
+            const D8 b = cost_both4(sCost, sExp, yreg[h], D4{v[0], v[1], v[2], v[3]});
+            cs[0] += rv ? b.c.a : 0.0;
+            cs[1] += rv ? b.c.b : 0.0;
+            cs[2] += rv ? b.c.c : 0.0;
+            cs[3] += rv ? b.c.d : 0.0;
+            v[0] = b.d.a;
+            v[1] = b.d.b;
+            v[2] = b.d.c;
+            v[3] = b.d.d;
+          } else if (sums_direct) {
             if (gauss_cost) {
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
@@ -709,7 +748,9 @@ __global__ void __launch_bounds__(NTHREADS, 1)
             }
           }
           if (EPI == PLS_EPI_COST) continue;  // sums only
-          if (gauss_direct || gauss_store) {
+          if (EPI == PLS_EPI_COST_DERIVATIVE_AND_COST && sums_direct && !gauss_cost) {
+            // (derivatives already in v)
+          } else if (gauss_direct || gauss_store) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) v[e] = inv_noise * (v[e] - yreg[h]);
           } else if (store_direct) {
@@ -724,7 +765,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
           if (col + 3 < cols_here) {
             if (wide_store) {
               asm volatile("st.global.L2::cache_hint.v4.f64 [%0], {%1,%2,%3,%4}, %5;" ::"l"(orow + col), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]),
-                           "l"(pol_store)
+                           "l"(pol_stream)
                            : "memory");
             } else {
               double2* dst = reinterpret_cast<double2*>(orow + col);
