@@ -232,8 +232,50 @@ def ipb_runs():
     print("ipb: cond(k(Z,Z)) =", float(torch.linalg.cond(basis.base_gram_induce)), "energy", pls.calculate_energy_potential(p))
 
 
+def runner_runs():
+    """experiments/runners.py:331-446 `train_pls_runner` (step-size search around train_pls; metric "loss") run UNMODIFIED.  Its
+    module imports the plotting layer (matplotlib is not installed): the names are satisfied by empty placeholder modules, no
+    plotting function is called (plot_energy_potential_path=None).  The runner also evaluates pls.predict on the training inputs
+    for every finite run (whatever the metric); set_seed(seed) at the start of every search makes the trainings independent of it."""
+    import types
+
+    class _Placeholder(types.ModuleType):
+        def __getattr__(self, name):  # plt.Figure, plt.Axes, ... appear in annotations of the plotting layer only
+            if name.startswith("__"):
+                raise AttributeError(name)
+            return type(name, (), {})
+
+    for name in ("matplotlib", "matplotlib.animation", "matplotlib.pyplot"):
+        sys.modules.setdefault(name, _Placeholder(name))
+    sys.modules["matplotlib"].animation = sys.modules["matplotlib.animation"]
+    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    from experiments.data import Data, ExperimentData, ProblemType  # noqa: E402
+    from experiments.runners import train_pls_runner  # noqa: E402
+
+    g = torch.Generator().manual_seed(33)
+    n, d, m, j = 90, 2, 8, 10
+    x = torch.randn(n, d, generator=g)
+    z = x[torch.randperm(n, generator=g)[:m]].clone()
+    ls = torch.tensor([0.9, 1.3])
+    kernel = make_kernel(ls, 1.2, ard=d)
+    basis = OrthonormalBasis(kernel=PLSKernel(base_kernel=kernel, approximation_samples=z), x_induce=z, x_train=x, eigenvalue_threshold=1e-6)
+    y = torch.sin(x.sum(1)) + 0.1 * torch.randn(n, generator=g)
+    pls = PLS(basis=basis, cost=GaussianCost(observation_noise=0.2, y_train=y, link_function=IdentityLinkFunction()))
+    p0 = pls.initialise_particles(number_of_particles=j, seed=4)
+    data = ExperimentData(name="synthetic", problem_type=ProblemType.REGRESSION, full=Data(x=x, y=y), train=Data(x=x, y=y, name="train"))
+    kw = dict(simulation_duration=0.04, maximum_number_of_steps=160, early_stopper_patience=0.01, number_of_step_searches=4,
+              step_size_upper=2e-3, minimum_change_in_energy_potential=1e-4, seed=11)
+    particles, best_lr, epochs = train_pls_runner(pls=pls, particle_name="p", experiment_data=data, particles=p0.clone(),
+                                                  metric_to_optimise="loss", **kw)
+    np.savez(os.path.join(HERE, "runner_runs.npz"), x=x.numpy(), z=z.numpy(), y=y.numpy(), lengthscale=ls.numpy(), outputscale=1.2,
+             observation_noise=0.2, threshold=1e-6, eigenvalues=basis.eigenvalues.numpy(), eigenvectors=basis.eigenvectors.numpy(),
+             p0=p0.numpy(), particles=particles.numpy(), best_lr=float(best_lr), epochs=int(epochs),
+             **{f"kw__{k}": v for k, v in kw.items()})
+    print("train_pls_runner: best_lr", best_lr, "epochs", epochs, "E", pls.calculate_energy_potential(particles))
+
+
 if __name__ == "__main__":
     # selector_scale takes ~15 min and 10 GB of host memory: run it by name
-    which = sys.argv[1:] or ["readme_demo", "one_step_all_costs", "selector_runs", "train_loop_runs", "ipb_runs"]
+    which = sys.argv[1:] or ["readme_demo", "one_step_all_costs", "selector_runs", "train_loop_runs", "ipb_runs", "runner_runs"]
     for name in which:
         globals()[name]()

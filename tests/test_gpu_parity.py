@@ -668,6 +668,35 @@ def test_step_size_search_runner_and_checkpoint(b200, tmp_path):
         torch.set_default_dtype(torch.float32)
 
 
+def test_step_size_search_runner_against_reference_run(b200, golden_dir):
+    """runners.train_pls_runner against a run of the reference's OWN experiments/runners.py:331-446 (tests/golden/make_golden.py
+    runner_runs; metric "loss", four log-spaced step sizes from the same particles and seed): the same best step size, the
+    same number of accepted epochs and the same particles."""
+    from projected_langevin_sampling_b200.runners import train_pls_runner
+
+    torch.set_default_dtype(torch.float64)
+    try:
+        costs, links = _costs_mod()
+        g = np.load(os.path.join(golden_dir, "runner_runs.npz"))
+        x, z = torch.from_numpy(g["x"]), torch.from_numpy(g["z"])
+        kernel = b200.ScaleKernel(b200.RBFKernel(ard_num_dims=2, lengthscale=torch.from_numpy(g["lengthscale"])),
+                                  outputscale=float(g["outputscale"]))
+        eig = (torch.from_numpy(g["eigenvalues"]), torch.from_numpy(g["eigenvectors"]))
+        basis = b200.OrthonormalBasis(b200.PLSKernel(kernel, z), z, x, eigenvalue_threshold=float(g["threshold"]),
+                                      eigendecomposition=eig, verbose=False)
+        pls = b200.PLS(basis, costs.GaussianCost(observation_noise=float(g["observation_noise"]), y_train=torch.from_numpy(g["y"]),
+                                                 link_function=links.IdentityLinkFunction()))
+        kw = {k[4:]: (int(g[k]) if k[4:] in ("maximum_number_of_steps", "number_of_step_searches", "seed") else float(g[k]))
+              for k in g.files if k.startswith("kw__")}
+        hist = {}
+        got_p, got_lr, got_n = train_pls_runner(pls, torch.from_numpy(g["p0"]).cuda(), energy_potentials_history=hist, **kw)
+        assert got_lr == float(g["best_lr"]) and got_n == int(g["epochs"])
+        assert len(hist) == kw["number_of_step_searches"]  # every search ran (no early break in the reference run either)
+        assert rel_err(got_p, torch.from_numpy(g["particles"])) < 1e-9  # 160 epochs of round-off growth on a 1e-10 step
+    finally:
+        torch.set_default_dtype(torch.float32)
+
+
 # ---- InducingPointBasis ("next" row) ---------------------------------------------------------------------------------------
 def test_ipb_reference_vectors(b200):  # reference tests/test_basis.py:98-116,248-269,369-387,495-519 (linear mock kernel)
     y2 = torch.tensor([2.1, 3.3])
