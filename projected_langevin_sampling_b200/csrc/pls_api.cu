@@ -94,6 +94,7 @@ int pls_ctx_create(int device, pls_ctx** out) {
   c->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
   if (const char* env = getenv("PLS_B200_TILE_RT")) c->tile_rt = atoi(env);
   if (const char* env = getenv("PLS_B200_TILE_NS")) c->tile_ns = atoi(env);
+  if (const char* env = getenv("PLS_B200_FUSED_FUNCTOR")) c->fused_functor = atoi(env);
   *out = c;
   return 0;
 }

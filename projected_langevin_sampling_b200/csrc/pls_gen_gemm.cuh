@@ -722,7 +722,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
           const int64_t r = row0 + (warp * RT + h) * 8 + g;
           const bool rv = r < p.n_rows;
           double v[4] = {acc[h][2 * pr][0], acc[h][2 * pr + 1][0], acc[h][2 * pr][1], acc[h][2 * pr + 1][1]};
-          if (EPI == PLS_EPI_COST_DERIVATIVE_AND_COST && sums_direct && !gauss_cost) {  // both from one specialised call
+          if (EPI == PLS_EPI_COST_DERIVATIVE_AND_COST && sums_direct && !gauss_cost && p.both) {  // both from one specialised call
             const D8 b = cost_both4(sCost, sExp, yreg[h], D4{v[0], v[1], v[2], v[3]});
             cs[0] += rv ? b.c.a : 0.0;
             cs[1] += rv ? b.c.b : 0.0;
@@ -748,7 +748,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
             }
           }
           if (EPI == PLS_EPI_COST) continue;  // sums only
-          if (EPI == PLS_EPI_COST_DERIVATIVE_AND_COST && sums_direct && !gauss_cost) {
+          if (EPI == PLS_EPI_COST_DERIVATIVE_AND_COST && sums_direct && !gauss_cost && p.both) {
             // (derivatives already in v)
           } else if (gauss_direct || gauss_store) {
 #pragma unroll
@@ -929,6 +929,7 @@ cudaError_t launch_one(const pls_ctx* ctx, GenGemmParams p, cudaStream_t stream)
   size_t smem = gen_gemm_smem_bytes<RT>(p.sp);
   if ((int64_t)smem > ctx->max_smem_optin) return cudaErrorInvalidConfiguration;
   p.wbuf_ok = 0;
+  p.both = ctx->fused_functor;
   if (!BACKWARD && (int64_t)gen_gemm_smem_bytes_wbuf<RT>(p.sp) <= ctx->max_smem_optin) {
     if (gen_gemm_smem_bytes_wbuf<RT>(p.sp) > smem) smem = gen_gemm_smem_bytes_wbuf<RT>(p.sp);
     p.wbuf_ok = 1;

@@ -16,6 +16,7 @@ struct pls_ctx {
   int max_smem_optin = 0;
   const uint64_t* step_counter = nullptr;  // device counter added to pls_project_update_f64's `step` (pls_set_step_counter)
   int tile_rt = 0;  // 0 = choose per launch from the particle count; 1 / 2 force a tile shape (PLS_B200_TILE_RT, tests)
+  int fused_functor = 1;  // fused training epilogue: one call for cost values + derivatives (0: two calls; PLS_B200_FUSED_FUNCTOR, A/B runs)
   int tile_ns = 0;  // 0 = park a second accumulator set in tensor memory whenever the shape allows; 1 = never (PLS_B200_TILE_NS, tests)
   std::string error;
   // pls_profile_begin / pls_profile_end: CUDA-event pairs around every launch of the hot kernel (role 0 forward, 1 backward)
@@ -48,6 +49,7 @@ struct GenGemmParams {
   int splits;    // backward role: number of reduction splits (gridDim = tiles * splits)
   int accumulate;
   int rt;  // tile shape: row tiles per warp (1: 64 x 256 CTA tile, 2: 128 x 128)
+  int both;             // set by the launcher: the fused derivative + cost epilogue evaluates both in one functor call
   int wbuf_ok;          // set by the launcher: shared memory has room for the per-warp cost sums of the register epilogue
   int tma3d;            // set by the launcher: the 3-D tensor map of the streamed matrix is usable
   int64_t full_blocks;  // set by the launcher: complete 16-column blocks per row of the streamed matrix (ldb / 16)

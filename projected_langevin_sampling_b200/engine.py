@@ -241,15 +241,18 @@ class LangevinEngine:
 
     def energy_and_gradient(self, particles: torch.Tensor, cost: nat.PlsCost, y: torch.Tensor) -> torch.Tensor:
         """One forward + backward: leaves G' in self.gm and returns the per-particle energy c_j + 1/2 sum_m P_mj^2 / lambda_m
-        of `particles` (J,) (PLS.calculate_energy_potential before its mean, orthonormal.py:110-126)."""
+        of `particles` (J,) (PLS.calculate_energy_potential before its mean, orthonormal.py:110-126).  With a `weights_fn`
+        (InducingPointBasis) the prior term is taken on W = k(Z, Z)^{-1} P, which the gradient has just left in self.w:
+        c_j + M/2 sum_m W_mj^2 (inducing_point.py:97-119; `inv_lambda` then holds the constant M)."""
         self.gradient(particles, cost, y, with_cost=True)
+        prior_of = self.w[:, : self.j] if self.weights_fn is not None else particles
         if self._neq_cost is not None:  # Gaussian shortcut: the cost sums are complete on every rank already
-            return ops.energy_terms(self.ctx, self._neq_cost.reshape(1, -1).contiguous(), self.j, particles, self.inv_lambda)
+            return ops.energy_terms(self.ctx, self._neq_cost.reshape(1, -1).contiguous(), self.j, prior_of, self.inv_lambda)
         c = self._cost_sums  # sum_n c(y_n, F[n][j]) of the SAME forward pass, written by pls_grad_f64
         if self.gradient_reduce is not None:  # rows are sharded: the cost sums are partial over this rank's rows, the prior term is not
             c = c.clone()
             self.gradient_reduce(c)
-        return ops.energy_terms(self.ctx, c.reshape(1, -1), self.j, particles, self.inv_lambda)
+        return ops.energy_terms(self.ctx, c.reshape(1, -1), self.j, prior_of, self.inv_lambda)
 
     def _zero_row(self) -> torch.Tensor:
         if self._zeros is None:

@@ -137,22 +137,30 @@ class InducingPointBasis(PLSBasis):
         partial = ops.as_device_f64(cost, p.device).reshape(1, j)
         return ops.energy_terms(self.ctx, partial, j, w, self._m_over).mean().item()  # 1/2 sum w^2 * M
 
-    def _noise(self, particles: torch.Tensor, noise) -> Optional[torch.Tensor]:
+    def _noise(self, particles: torch.Tensor, noise, philox: Optional[Tuple[int, int, int]] = None) -> Optional[torch.Tensor]:
         """e ~ N(0, k(Z, Z)) (M, J).  noise=None: the reference's draw (one torch.normal((M, J)) on the global CPU generator,
-        samplers.py:27-35); a tensor: the STANDARD normal z to colour; False: no noise."""
+        samplers.py:27-35); a tensor: the STANDARD normal z to colour; False: no noise; philox=(seed, step, j_global_offset):
+        z from the device-side Philox4x32-10 stream keyed on the global (row, particle), as the OrthonormalBasis uses it."""
         if noise is False:
             return None
-        z = langevin_noise(particles.shape[0], particles.shape[1]) if noise is None else noise
+        if philox is not None:
+            seed, step, j_off = philox
+            z = ops.philox_normal(self.ctx, seed, step, particles.shape[0], particles.shape[1], j_off, device=particles.device)
+        else:
+            z = langevin_noise(particles.shape[0], particles.shape[1]) if noise is None else noise
         z = ops.as_device_f64(z, particles.device)
         e, _ = ops.alloc_matrix(particles.shape[0], particles.shape[1], particles.device)
         ops.gemm(self.ctx, self._noise_factor, z, e)  # V sqrt(lambda) z
         return e[:, : particles.shape[1]]
 
-    def _combine(self, particles: torch.Tensor, gm: torch.Tensor, step_size: float, noise, in_place: bool) -> torch.Tensor:
-        """-eta G' - eta M k(Z,Z)^{-1} P + sqrt(2 eta) e   (:140-149)."""
+    def _combine(self, particles: torch.Tensor, gm: torch.Tensor, step_size: float, noise, in_place: bool,
+                 philox: Optional[Tuple[int, int, int]] = None, w: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """-eta G' - eta M k(Z,Z)^{-1} P + sqrt(2 eta) e   (:140-149).  w: k(Z,Z)^{-1} P when the caller already holds it (the
+        gradient leaves it in the engine's W workspace)."""
         j = particles.shape[1]
-        w = self._solve(particles).contiguous()
-        e = self._noise(particles, noise)
+        if w is None:
+            w = self._solve(particles).contiguous()
+        e = self._noise(particles, noise, philox)
         out = particles if in_place else torch.empty_like(particles, memory_format=torch.contiguous_format)
         zero = e if e is not None else w
         return ops.lincomb3(self.ctx, -step_size, gm, -step_size * self.approximation_dimension, w,
@@ -177,8 +185,6 @@ class InducingPointBasis(PLSBasis):
     def fused_particle_update(self, particles: torch.Tensor, cost, step_size: float, noise=None, in_place: bool = False,
                               philox: Optional[Tuple[int, int, int]] = None) -> torch.Tensor:
         """One Langevin step without materialising k(X, Z) or the (N, J) prediction."""
-        if philox is not None:
-            raise ValueError("InducingPointBasis: the device-side Philox stream is not wired up (the noise is coloured by k(Z, Z))")
         p = self._particles(particles)
         if in_place and p is not particles:
             raise ValueError("in_place needs float64 CUDA particles with unit column stride")
@@ -187,7 +193,12 @@ class InducingPointBasis(PLSBasis):
         ), f"Particles have shape {p.shape} but requires ({self.approximation_dimension}, J) dimension."
         eng = self.engine(p.shape[1])
         gm = eng.gradient(p, cost.native(), cost.y_device(p.device))  # enqueued first: the host noise draw overlaps it
-        return self._combine(p, gm, float(step_size), noise, in_place=in_place)
+        return self._combine(p, gm, float(step_size), noise, in_place=in_place, philox=philox, w=eng.w[:, : p.shape[1]])
+
+    def apply_langevin_update(self, eng: LangevinEngine, p: torch.Tensor, step_size: float,
+                              philox: Optional[Tuple[int, int, int]] = None) -> None:
+        """In-place update from the gradient and W = k(Z, Z)^{-1} P that eng.gradient / eng.energy_and_gradient left behind."""
+        self._combine(p, eng.gm, step_size, None, in_place=True, philox=philox, w=eng.w[:, : p.shape[1]])
 
     # ---- prediction side (:152-240) -----------------------------------------------------------------------------------------
     def sample_predictive_noise(self, particles: torch.Tensor, x: torch.Tensor) -> torch.Tensor:

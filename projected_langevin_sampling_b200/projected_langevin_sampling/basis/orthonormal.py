@@ -186,6 +186,16 @@ class OrthonormalBasis(PLSBasis):
         mode, xi = self._noise(p, None)
         return eng.apply_update(p, float(step_size), out, mode, xi=xi, in_place=in_place)
 
+    def apply_langevin_update(self, eng: LangevinEngine, p: torch.Tensor, step_size: float,
+                              philox: Optional[Tuple[int, int, int]] = None) -> None:
+        """In-place update from the gradient eng.gradient / eng.energy_and_gradient left in the engine (the second half of a step)."""
+        if philox is None:
+            xi = ops.as_device_f64(langevin_noise(p.shape[0], p.shape[1]), p.device)  # samplers.py:27-35 via orthonormal.py:141-145
+            eng.apply_update(p, step_size, p, nat.NOISE_GIVEN, xi=xi, in_place=True)
+        else:
+            seed, step, j_off = philox
+            eng.apply_update(p, step_size, p, nat.NOISE_PHILOX, seed=seed, step_index=step, j_global_offset=j_off, in_place=True)
+
     # ---- prediction side (reference: orthonormal.py:161-244) -------------------------------------------------------------
     def sample_predictive_noise(self, particles: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
         x = ops.as_device_f64(x if x.dim() > 1 else x.unsqueeze(-1), self.x_induce.device)

@@ -13,11 +13,8 @@ from typing import List, Optional, Tuple
 
 import torch
 
-from . import _native as nat
-from . import ops
 from .early_stopper import EarlyStopper
 from .projected_langevin_sampling import PLS
-from .samplers import langevin_noise
 
 
 def train_pls(pls: PLS, particles: torch.Tensor, number_of_epochs: int, step_size: float, early_stopper_patience: float,
@@ -27,26 +24,13 @@ def train_pls(pls: PLS, particles: torch.Tensor, number_of_epochs: int, step_siz
     CUDA tensor (the reference's `particles += particle_update`); otherwise the result is copied back into it.
     philox_seed=None replays the reference's noise (one torch.normal((M_k, J)) per epoch on the global CPU generator);
     an integer switches to the on-device Philox stream keyed on (seed, epoch, row, j_global_offset + column).
+    Both bases run the fused epoch: for the InducingPointBasis the prior term of the energy is taken on the
+    W = k(Z, Z)^{-1} P that the gradient has just formed (inducing_point.py:97-119).
     `tqdm_desc` is accepted for signature compatibility (no progress bar is drawn)."""
     del tqdm_desc
     basis, cost = pls.basis, pls.cost
     if not pls._fused():
         raise TypeError("train_pls needs a basis and a cost with a CUDA implementation (there is no CPU fallback)")
-    if not hasattr(basis, "scaled_eigenvectors"):  # InducingPointBasis: the reference-shaped loop (update, then energy)
-        if philox_seed is not None:
-            raise ValueError("philox_seed needs an OrthonormalBasis")
-        p = basis._particles(particles)
-        energy_potentials: List[float] = []
-        early_stopper = EarlyStopper(patience=early_stopper_patience)
-        for _ in range(number_of_epochs):
-            basis.fused_particle_update(p, cost, float(step_size), in_place=True)
-            energy = pls.calculate_energy_potential(p)
-            if early_stopper.should_stop(loss=energy, step_size=float(step_size)):
-                break
-            energy_potentials.append(energy)
-        if p is not particles:
-            particles.copy_(p.to(device=particles.device, dtype=particles.dtype))
-        return particles, energy_potentials
     p = basis._particles(particles)  # float64, on the device, unit column stride (a copy if `particles` is not)
     assert (
         p.shape[0] == basis.approximation_dimension
@@ -66,12 +50,9 @@ def train_pls(pls: PLS, particles: torch.Tensor, number_of_epochs: int, step_siz
                 stopped = True  # the previous epoch's update stays, its energy is not recorded (trainers.py:159-161)
                 break
             energy_potentials.append(energy)
-        if philox_seed is None:
-            xi = ops.as_device_f64(langevin_noise(p.shape[0], p.shape[1]), p.device)  # samplers.py:27-35 via orthonormal.py:141-145
-            eng.apply_update(p, step_size, p, nat.NOISE_GIVEN, xi=xi, in_place=True)
-        else:
-            eng.apply_update(p, step_size, p, nat.NOISE_PHILOX, seed=philox_seed, step_index=epoch,
-                             j_global_offset=j_global_offset, in_place=True)
+        # both bases: the update from the gradient (and, InducingPointBasis, from W = k(Z, Z)^{-1} P) that pass left in the engine;
+        # the reference's torch.normal((M, J)) draw per epoch, or the device-side Philox stream
+        basis.apply_langevin_update(eng, p, step_size, None if philox_seed is None else (philox_seed, epoch, j_global_offset))
     if not stopped and number_of_epochs > 0:
         energy = pls.calculate_energy_potential(p)
         if not early_stopper.should_stop(loss=energy, step_size=step_size):

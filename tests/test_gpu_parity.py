@@ -775,6 +775,53 @@ def test_ipb_step_matches_oracle_at_size(b200):
         torch.set_default_dtype(torch.float32)
 
 
+def test_ipb_fused_training_loop_and_philox(b200):
+    """InducingPointBasis through train_pls: the fused epoch (energy and gradient from one forward, the prior term on the
+    W = k(Z, Z)^{-1} P that pass formed) equals the reference-shaped loop over calculate_particle_update +
+    calculate_energy_potential on the reference's noise stream; with the device-side Philox stream the run does not depend on
+    how the particles are split (the coloured noise is a column-wise product of V sqrt(lambda) with keyed normals)."""
+    from projected_langevin_sampling_b200.trainers import train_pls
+
+    torch.set_default_dtype(torch.float64)
+    try:
+        costs, links = _costs_mod()
+        g = torch.Generator().manual_seed(61)
+        n, d, m, j = 900, 2, 25, 40
+        x = 4 * torch.rand(n, d, generator=g) - 2
+        gx, gy = torch.meshgrid(torch.linspace(-2, 2, 5), torch.linspace(-2, 2, 5), indexing="ij")
+        z = torch.stack([gx.reshape(-1), gy.reshape(-1)], dim=1).double()
+        y = torch.sin(x.sum(1)) + 0.1 * torch.randn(n, generator=g)
+        y_induce = torch.sin(z.sum(1))
+        kernel = b200.ScaleKernel(b200.RBFKernel(ard_num_dims=d, lengthscale=torch.tensor([0.6, 0.7])), outputscale=1.2)
+        basis = b200.InducingPointBasis(b200.PLSKernel(kernel, z), z, y_induce, x, dc_budget_bytes=256 * 40 * 8)
+        pls = b200.PLS(basis, costs.GaussianCost(observation_noise=0.3, y_train=y, link_function=links.IdentityLinkFunction()))
+        p0 = pls.initialise_particles(number_of_particles=j, seed=2, noise_only=False)
+        torch.manual_seed(9)
+        p_ref, e_ref = p0.clone().cuda(), []
+        for _ in range(5):
+            p_ref += pls.calculate_particle_update(p_ref, 5e-4)
+            e_ref.append(pls.calculate_energy_potential(p_ref))
+        torch.manual_seed(9)
+        p, energies = train_pls(pls, p0.clone().cuda(), 5, 5e-4, early_stopper_patience=10.0)
+        assert np.allclose(energies, e_ref, rtol=1e-11)
+        assert rel_err(p, p_ref) < 1e-11
+        # Philox: whole particle set vs two particle shards advanced separately
+        whole, e_whole = train_pls(pls, p0.clone().cuda(), 4, 5e-4, early_stopper_patience=10.0, philox_seed=123)
+        parts = []
+        for j0, j1 in ((0, 16), (16, j)):
+            part, _ = train_pls(pls, p0[:, j0:j1].clone().cuda(), 4, 5e-4, early_stopper_patience=10.0, philox_seed=123, j_global_offset=j0)
+            parts.append(part)
+        assert rel_err(torch.cat(parts, dim=1), whole) < 1e-12 and len(e_whole) == 4 and all(np.isfinite(e_whole))
+        assert not torch.equal(whole.cpu(), p.cpu())  # a different noise stream
+        q = p0.clone().cuda()
+        pls.step_(q, 5e-4, philox=(123, 0, 0))
+        again = p0.clone().cuda()
+        pls.step_(again, 5e-4, philox=(123, 0, 0))
+        assert torch.equal(q, again) and bool(torch.isfinite(q).all())
+    finally:
+        torch.set_default_dtype(torch.float32)
+
+
 def _mock_r_kernel(pkg, samples):
     """The reference tests' MockProjectedLangevinSamplingKernel (mockers/kernel.py:26-43): its forward is the base kernel."""
     from projected_langevin_sampling_b200.kernels import dense_gram
