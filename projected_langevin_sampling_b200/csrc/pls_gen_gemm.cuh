@@ -306,14 +306,18 @@ __global__ void __launch_bounds__(NTHREADS, 1)
   const int nchunks = (red_len + BK - 1) / BK;         // 32-point chunks per tile
   const int nblocks = nchunks * NS;                    // streamed blocks (pipeline stages) per tile: one per chunk and column half
   const int total_gc = my_tiles * nblocks;             // blocks this CTA streams, over all its tiles (the launcher checks the range)
+  // (32-bit unsigned arithmetic: this runs on ONE lane at every stage refill while the rest of its warp waits -- the 64-bit
+  // division it used to contain cost the slowest warp of the CTA several hundred cycles per block; the launcher checks the range)
+  const unsigned nct32 = (unsigned)n_col_tiles;
   auto tile_coords = [&](int ti, int64_t& rt, int64_t& ct) {
     if (BACKWARD) {
       rt = bw_rt;
       ct = bw_ct;
     } else {
-      const int64_t tile = (int64_t)blockIdx.x + (int64_t)ti * gridDim.x;
-      ct = tile % n_col_tiles;
-      rt = tile / n_col_tiles;
+      const unsigned tile = blockIdx.x + (unsigned)ti * gridDim.x;
+      const unsigned q = tile / nct32;
+      ct = (int64_t)(tile - q * nct32);
+      rt = (int64_t)q;
     }
   };
 
@@ -348,7 +352,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
   // that block carries the reduction points of chunk c + 1 (read from the stage in use, before it is released: no warp ever
   // waits on a block ahead of the one it multiplies); the tile's first block carries the points of chunk 0 for the prologue.
   auto issue = [&](int gc) {
-    const int ti = gc / nblocks;
+    const int ti = (int)((unsigned)gc / (unsigned)nblocks);
     const int b = gc - ti * nblocks;
     const int c = (NS == 2) ? (b >> 1) : b;
     const int half = (NS == 2) ? (((c & 1) != 0) != ((b & 1) != 0) ? 1 : 0) : 0;
@@ -358,7 +362,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     tile_coords(ti, rt, ct);
     const int64_t j0 = ct * BJT + half * BJ;
     const bool use3d = p.tma3d && (j0 + BJ <= p.full_blocks * 16 || p.full_blocks * 16 == p.ldb);
-    const int stage = gc % STAGES;
+    const int stage = (int)((unsigned)gc % (unsigned)STAGES);
     const int64_t k0 = begin + (int64_t)c * BK;
     const int64_t kp0 = begin + (int64_t)cp * BK;
     const int kc = (int)((end - kp0 < BK) ? (end - kp0) : BK);  // points copied
@@ -923,6 +927,7 @@ cudaError_t launch_one(const pls_ctx* ctx, GenGemmParams p, cudaStream_t stream)
     if (grid > ctx->sm_count) grid = ctx->sm_count;  // persistent forward: one CTA per SM walks the tiles
     // the kernel counts the chunks a CTA streams over all its tiles in 32 bits
     if (grid > 0 && ((tiles + grid - 1) / grid) * ((p.red_total + BK - 1) / BK) * NS > 2147483647LL) return cudaErrorInvalidConfiguration;
+    if (tiles + grid > 2147483647LL) return cudaErrorInvalidConfiguration;  // the kernel numbers its tiles in 32 bits
   }
   if (grid <= 0 || p.red_total <= 0) return cudaSuccess;
   if (grid > 2147483647LL) return cudaErrorInvalidConfiguration;

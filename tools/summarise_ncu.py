@@ -22,6 +22,9 @@ KEYS = [
     "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_tensor_op_dmma.sum",
     "smsp__inst_executed_pipe_fp64.sum", "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
     "smsp__cycles_active.avg", "sm__cycles_elapsed.avg", "smsp__warps_active.avg.per_cycle_active",
+    # the FP64 tensor sub-pipe (DMMA) and the pipe it shares with DFMA/DADD/DMUL ("shared pipe"): busy cycles and instruction counts
+    "sm__pipe_tensor_subpipe_dmma_cycles_active.avg.pct_of_peak_sustained_elapsed", "sm__pipe_shared_cycles_active.avg.pct_of_peak_sustained_elapsed",
+    "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_elapsed", "sm__inst_executed_pipe_tensor_subpipe_dmma.sum", "sm__inst_executed_pipe_fp64.sum",
 ]
 
 
