@@ -109,9 +109,10 @@ int pls_forward_tile_rows(const pls_ctx* ctx, int64_t j);
  * 0 = choose per launch (default).  Benchmarks and tests only; the environment variable PLS_B200_TILE_RT does the same. */
 void pls_set_tile_shape(pls_ctx* ctx, int rt);
 /* accumulator sets per CTA tile of the generated-Gram kernels: ns = 0 (default) parks a second 256-column accumulator set in
- * tensor memory (64 x 512 tiles: every generated Gram value feeds 512 particles) whenever the particle slice is an even number
- * of 256-column tiles; ns = 1 never does.  Results are bit-identical either way (each column is accumulated in the same
- * order).  Benchmarks and tests only; the environment variable PLS_B200_TILE_NS does the same. */
+ * tensor memory (64 x 512 tiles: every generated Gram value feeds 512 particles) when the particle slice is an even number of
+ * 256-column tiles and the launch is large enough for the wider tile to pay (>= 8 chunks per tile, enough tiles for every SM);
+ * ns = 1 never does; ns = 2 does whenever the shape allows it.  Results are bit-identical either way (each column is accumulated
+ * in the same order).  Benchmarks and tests only; the environment variable PLS_B200_TILE_NS does the same. */
 void pls_set_tile_sets(pls_ctx* ctx, int ns);
 
 /* ---- one-time setup ------------------------------------------------------------------------------------------ */

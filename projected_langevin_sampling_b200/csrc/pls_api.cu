@@ -158,7 +158,7 @@ int pls_backward_splits(const pls_ctx* ctx, int64_t n_rows, int64_t m, int64_t j
   // stages), and among the admissible counts the one that fills whole waves best (ties: fewer splits, less Gp traffic).
   const int sms = (ctx && ctx->sm_count > 0) ? ctx->sm_count : 148;
   const int rt = pls::choose_tile_rt(ctx, j);
-  const int64_t br = pls::tile_rows(rt), bj = pls::tile_cols(rt) * pls::choose_tile_ns(ctx, j, false);  // (the generated-Gram default)
+  const int64_t br = pls::tile_rows(rt), bj = pls::tile_cols(rt) * pls::choose_tile_ns(ctx, j, false, m, n_rows, true);  // (the generated-Gram default)
   const int64_t tiles = ((m + br - 1) / br) * ((j + bj - 1) / bj);
   if (tiles <= 0 || n_rows <= 0) return 1;
   const int64_t chunks = (n_rows + pls::BK - 1) / pls::BK;
@@ -192,7 +192,7 @@ void pls_set_tile_shape(pls_ctx* ctx, int rt) {
 }
 
 void pls_set_tile_sets(pls_ctx* ctx, int ns) {
-  if (ctx) ctx->tile_ns = (ns == 1) ? 1 : 0;
+  if (ctx) ctx->tile_ns = (ns == 1 || ns == 2) ? ns : 0;
 }
 
 int pls_prepare_points_f64(pls_ctx* ctx, int kernel_id, const double* x, int64_t n, int d, int64_t ldx,

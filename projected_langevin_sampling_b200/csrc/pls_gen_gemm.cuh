@@ -351,18 +351,14 @@ __global__ void __launch_bounds__(NTHREADS, 1)
   // needs a swap of the accumulator sets.  The Gram values of chunk c + 1 are formed during the SECOND block of chunk c, so
   // that block carries the reduction points of chunk c + 1 (read from the stage in use, before it is released: no warp ever
   // waits on a block ahead of the one it multiplies); the tile's first block carries the points of chunk 0 for the prologue.
-  auto issue = [&](int gc) {
-    const int ti = (int)((unsigned)gc / (unsigned)nblocks);
-    const int b = gc - ti * nblocks;
+  // issue_block: block b of a tile in column position ct_i into `stage`.
+  auto issue_block = [&](int ct_i, int b, int stage) {
     const int c = (NS == 2) ? (b >> 1) : b;
     const int half = (NS == 2) ? (((c & 1) != 0) != ((b & 1) != 0) ? 1 : 0) : 0;
     const int cp = (NS == 2) ? ((b == 0) ? 0 : ((b & 1) ? c + 1 : nchunks)) : c;  // chunk whose points travel with this block
     const bool with_points = KSRC != KSRC_CACHED && cp < nchunks;
-    int64_t rt, ct;
-    tile_coords(ti, rt, ct);
-    const int64_t j0 = ct * BJT + half * BJ;
+    const int64_t j0 = (int64_t)ct_i * BJT + half * BJ;
     const bool use3d = p.tma3d && (j0 + BJ <= p.full_blocks * 16 || p.full_blocks * 16 == p.ldb);
-    const int stage = (int)((unsigned)gc % (unsigned)STAGES);
     const int64_t k0 = begin + (int64_t)c * BK;
     const int64_t kp0 = begin + (int64_t)cp * BK;
     const int kc = (int)((end - kp0 < BK) ? (end - kp0) : BK);  // points copied
@@ -376,6 +372,30 @@ __global__ void __launch_bounds__(NTHREADS, 1)
       for (int blk = 0; blk < NPR; ++blk) tma_load_2d(dst + blk * BLOCK_BYTES, &tm2, (int)j0 + 16 * blk, (int)k0, bar);
     }
     if (with_points) bulk_g2s(sP + stage * BK * sp, p.red_aug + kp0 * sp, (uint32_t)(kc * sp * 8), bar);  // (sp = 0 when cached)
+  };
+  // general form: block gc of this CTA's stream (two divisions: used for the first STAGES blocks and for tiles shorter than the pipeline)
+  auto issue = [&](int gc) {
+    const int ti = (int)((unsigned)gc / (unsigned)nblocks);
+    int64_t rt, ct;
+    tile_coords(ti, rt, ct);
+    issue_block((int)ct, gc - ti * nblocks, (int)((unsigned)gc % (unsigned)STAGES));
+  };
+  // refill of the stage a warp has just released with the block STAGES further on: same stage; the block belongs to the tile the
+  // warp is in (column position ct_cur) or to this CTA's next tile, gridDim.x tiles further on -- no division on this path, which
+  // one lane runs while the rest of its warp waits
+  const int gstep = BACKWARD ? 0 : (int)(gridDim.x % nct32);
+  auto issue_from = [&](int gc_cur, int ct_cur, int b_cur, int stage) {
+    int b = b_cur + STAGES, ct_i = ct_cur;
+    if (b >= nblocks) {
+      b -= nblocks;
+      ct_i += gstep;
+      if (ct_i >= (int)nct32) ct_i -= (int)nct32;
+      if (b >= nblocks) {
+        issue(gc_cur + STAGES);
+        return;
+      }
+    }
+    issue_block(ct_i, b, stage);
   };
   if (tid == 0) {
     for (int gc = 0; gc < STAGES && gc < total_gc; ++gc) issue(gc);
@@ -589,7 +609,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
       if (lane == 0) {
         if (atom_add_shared(&released[stage], 1u) == NWARPS - 1) {
           released[stage] = 0;
-          if (gc + STAGES < total_gc && (BACKWARD || direct || more)) issue(gc + STAGES);
+          if (gc + STAGES < total_gc && (BACKWARD || direct || more)) issue_from(gc, (int)ct, c, stage);
         }
       }
       stage = nstage;
@@ -609,12 +629,12 @@ __global__ void __launch_bounds__(NTHREADS, 1)
         mma_step(bgrp + off1, k[q][1]);
       }
     };
-    auto release_block = [&]() {  // as in run_chunk: the last warp to release a stage refills it (no deferral: register epilogues only)
+    auto release_block = [&](int b_cur) {  // as in run_chunk: the last warp to release a stage refills it (no deferral: register epilogues only)
       __syncwarp();
       if (lane == 0) {
         if (atom_add_shared(&released[stage], 1u) == NWARPS - 1) {
           released[stage] = 0;
-          if (gc + STAGES < total_gc) issue(gc + STAGES);
+          if (gc + STAGES < total_gc) issue_from(gc, (int)ct, b_cur, stage);
         }
       }
       stage = (stage + 1 == STAGES) ? 0 : stage + 1;
@@ -624,7 +644,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     auto run_pair = [&](int c, double (&k0)[LA][2][RT], double (&k1)[LA][2][RT]) {
       if (c > 0) mbar_wait(&full[stage], phase);  // (chunk 0: the tile prologue waited for this block, which carries its points)
       dmma_block(k0);
-      release_block();
+      release_block(2 * c);
       // park the finished half's accumulators, fetch the other half's (zero before its first block)
       if constexpr (NS == 2) {
         tmem_store64(tslot + (unsigned)(c & 1) * 128u, acc[0]);
@@ -642,7 +662,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
       mbar_wait(&full[stage], phase);
       if (c + 1 < nchunks) gram_block(sP + stage * BK * sp, 0, (c + 1) * BK + 2 * t, k1);  // the next chunk's points came with this block
       dmma_block(k0);
-      release_block();
+      release_block(2 * c + 1);
     };
 #pragma unroll 1
     for (int c = 0; c < nchunks;) {
@@ -963,7 +983,7 @@ cudaError_t launch_role(const pls_ctx* ctx, const GenGemmParams& p, cudaStream_t
   const bool rbf = (p.kernel_id == PLS_KERNEL_RBF);
   // 64 x 512 tiles with the second accumulator set parked in tensor memory (NS = 2): RBF, an even number of 256-column tiles,
   // and an epilogue that runs from registers (the cost-sum epilogues need room for the per-warp sums and > STAGES blocks per tile)
-  if (rbf && p.rt == 1 && choose_tile_ns(ctx, p.j, false) == 2) {
+  if (rbf && p.rt == 1 && choose_tile_ns(ctx, p.j, false, p.n_rows, p.red_total, BW) == 2) {
     const bool sums = ROLE == PLS_EPI_COST || ROLE == PLS_EPI_COST_DERIVATIVE_AND_COST;
     const bool sums_from_registers = (int64_t)gen_gemm_smem_bytes_wbuf<1>(p.sp) <= ctx->max_smem_optin && 2 * ((p.red_total + BK - 1) / BK) > STAGES;
     if (!sums || sums_from_registers) return launch_one<NKD, BW, KSRC_RBF, 1, ROLE, 2>(ctx, p, stream);

@@ -68,10 +68,21 @@ inline int choose_tile_rt(const pls_ctx* ctx, int64_t j) {
 }
 
 // accumulator sets per CTA tile of the generated-Gram kernels: 2 (64 x 512 tile, the second set parked in tensor memory) when the
-// particle slice is an even number of 256-column tiles, else 1.  The cached-Gram kernels generate nothing and stay at 1.
-inline int choose_tile_ns(const pls_ctx* ctx, int64_t j, bool cached) {
+// particle slice is an even number of 256-column tiles AND the launch is large enough for the wider tile to pay -- a tile of at
+// least 8 chunks (forward: M >= 256) and enough 64 x 512 tiles (times the splits the reduction allows) to keep every SM busy;
+// measured: C2 (M = 64, J = 1024) 4.66 M particle-updates/s with 256-column tiles against 3.35 M with 512-column ones, C3
+// (M = 256) and larger the other way round.  out_rows x j is the output, red_len the reduction length.  The cached-Gram kernels
+// generate nothing and stay at 1.  ctx->tile_ns: 0 = this rule, 1 = never, 2 = whenever the shape allows it (tests).
+inline int choose_tile_ns(const pls_ctx* ctx, int64_t j, bool cached, int64_t out_rows, int64_t red_len, bool backward) {
   if (cached || choose_tile_rt(ctx, j) != 1 || (ctx && ctx->tile_ns == 1)) return 1;
-  return (((j + 255) / 256) % 2 == 0) ? 2 : 1;
+  if (((j + 255) / 256) % 2 != 0) return 1;
+  if (ctx && ctx->tile_ns == 2) return 2;
+  const int64_t sms = (ctx && ctx->sm_count > 0) ? ctx->sm_count : 148;
+  const int64_t chunks = (red_len + 31) / 32;
+  const int64_t tiles = ((out_rows + 63) / 64) * ((j + 511) / 512);
+  if (!backward) return (chunks >= 8 && tiles >= 2 * sms) ? 2 : 1;
+  const int64_t max_splits = chunks / 8 > 1 ? chunks / 8 : 1;
+  return (tiles * max_splits >= 8 * sms) ? 2 : 1;
 }
 
 // Tensor maps of the streamed matrix b (rows x ldb doubles, 16-byte aligned, ldb even) for the hot kernel's stages of 32 rows

@@ -449,12 +449,13 @@ def test_parked_accumulators_are_bit_identical(ctx, n, m, d, j, ld, cost_name):
         torch.cuda.synchronize()
         return out
 
-    ctx.lib.pls_set_tile_sets(ctx.handle, 1)
     try:
+        ctx.lib.pls_set_tile_sets(ctx.handle, 1)  # never
         want = run_all()
+        ctx.lib.pls_set_tile_sets(ctx.handle, 2)  # whenever the shape allows (the default rule would skip these small launches)
+        got = run_all()
     finally:
         ctx.lib.pls_set_tile_sets(ctx.handle, 0)
-    got = run_all()
     k_xz = ops.gram(ctx, nat.KERNEL_RBF, xa, za, d)
     ref_f = k_xz @ w[:, :j]
     assert (want["f"][:, :j] - ref_f).abs().max().item() < 1e-12 * max(1.0, ref_f.abs().max().item())

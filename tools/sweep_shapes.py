@@ -28,10 +28,11 @@ def main():
         n = int(rng.integers(1, 90 if small else 3000))
         m = int(rng.integers(1, 40 if small else 600))
         d = int(rng.integers(1, 27))  # MAX_D = 26
-        j = int(rng.integers(1, 20 if small else 900))
+        j = int(rng.integers(1, 20 if small else (2100 if it % 5 == 1 else 900)))
         ld = j + (j & 1) + int(rng.choice([0, 2, 14, 30]))
         rt = int(rng.choice([0, 1, 2]))
         ctx.lib.pls_set_tile_shape(ctx.handle, rt)
+        ctx.lib.pls_set_tile_sets(ctx.handle, int(rng.choice([0, 1, 2])))  # 64 x 512 tiles (tensor-memory parking): rule / never / forced
         g = torch.Generator().manual_seed(int(rng.integers(1 << 30)))
         x = torch.randn(n, d, generator=g, dtype=torch.float64).cuda()
         z = torch.randn(m, d, generator=g, dtype=torch.float64).cuda()
@@ -83,6 +84,7 @@ def main():
                 print("FAIL", dict(n=n, m=m, d=d, j=j, ld=ld, rt=rt, cached=gram is not None), errs, untouched)
                 sys.exit(1)
     ctx.lib.pls_set_tile_shape(ctx.handle, 0)
+    ctx.lib.pls_set_tile_sets(ctx.handle, 0)
     print(f"sweep ok: {args.count} shapes x 2 Gram sources, worst scaled error {worst:.2e}")
 
 
