@@ -166,7 +166,7 @@ def base_config(workload: dict, world: int, grid: str) -> dict:
     """The part of `config` that both arms print verbatim (the CPU arm runs the same workload on one host)."""
     return {"workload": workload["label"], "N": workload["n"], "D": workload["d"], "M": workload["m"], "J_global": workload["j"],
             "cost": workload["cost"], "step_size": step_size_of(workload), "grid": grid, "n_gpus": world,
-            "l2": "per-step working set (the Dc chunk, up to 8 GiB written + read) exceeds the 126 MB L2; no flush needed"}
+            "l2": "per-step working set (the Dc chunk, N x J_local doubles written + read: GBs) exceeds the 126 MB L2; no flush needed"}
 
 
 def cpu_arm(workload: dict, steps: int, warmup: int) -> dict:
@@ -685,7 +685,7 @@ def main():
         "traffic_note": ("NOT measured in this run: DRAM bytes per launch (mean of the forward and backward roles) read from profiles/roofline_traffic.json, "
                          "one ncu --set full capture of this command" + (f" ({traffic_src})" if traffic_src else "") + ".  The step is TWO kernels "
                          "with an N_chunk x J round trip between them: the forward writes the cost-derivative chunk Dc to HBM once and the backward "
-                         "reads it once (8.6 GB each way per 262 144-row chunk at C4 -- ~500x SURVEY 8d's 0.15 GB/step minimum for a single-pass "
+                         f"reads it once ({chunk_rows * j_local * 8 / 1e9:.1f} GB each way per {chunk_rows}-row chunk here; at C4 ~66 GB per step, ~500x SURVEY 8d's 0.15 GB/step minimum for a single-pass "
                          "design, ~2 % of the HBM bandwidth, not the limiter: the kernels are FP64-pipe bound)"),
         "kernel": "pls::gen_gemm_kernel (forward + backward roles; FP64 DMMA.8x8x4, no tcgen05 kind exists for f64); Gram " + gram_note,
         "algorithmic_flops_per_step": 4.0 * n * m * j,

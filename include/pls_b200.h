@@ -247,7 +247,7 @@ int pls_flat_math_f64(pls_ctx* ctx, int op, const double* a, const double* b, in
  * pls/costs/<cost>.py, orthonormal.py:128-159) as ONE call over caller-owned workspaces: W = V~ P, the row-chunk loop
  * (forward with the cost derivative in its epilogue, backward), the split reduction and -- pls_step_f64 -- the update.
  * pls_step_plan_f64 (host only) fixes the chunking of the training rows and the layout of the workspace:
- *   dc_budget_bytes  bound on the only N-sized intermediate, the Dc chunk (<= 0: 8 GiB);
+ *   dc_budget_bytes  bound on the only N-sized intermediate, the Dc chunk (<= 0: 32 GiB -- the headline N = 1M x J = 4096 in one chunk);
  *   gram_mode        PLS_GRAM_GENERATED: Gram tiles regenerated inside the kernels, nothing N x M in memory (default path);
  *                    PLS_GRAM_STAGED:    k(X_c, Z) of the chunk in flight re-formed every step into a chunk-sized region of the
  *                                        workspace (pls_gram_fill_f64) and streamed by that chunk's two launches;

@@ -31,7 +31,7 @@ int pls_step_plan_f64(const pls_ctx* ctx, int64_t n, int64_t m, int64_t m_k, int
                       int with_cost, pls_step_plan* plan) {
   if (!plan || n < 0 || m < 1 || m_k < 0 || j < 1 || gram_mode < PLS_GRAM_GENERATED || gram_mode > PLS_GRAM_CACHED) return 1;
   std::memset(plan, 0, sizeof(*plan));
-  if (dc_budget_bytes <= 0) dc_budget_bytes = 8LL << 30;
+  if (dc_budget_bytes <= 0) dc_budget_bytes = 32LL << 30;
   plan->n = n;
   plan->m = m;
   plan->m_k = m_k;

@@ -12,7 +12,7 @@ One step (reference: PLS.calculate_particle_update, src/projected_langevin_sampl
     P += -eta V~^T G' - eta P / lambda + sqrt(2 eta) xi      pls_project_update_f64
 
 The N x J prediction matrix is never materialised; the only N x J intermediate is the Dc chunk (`dc_budget_bytes`, default
-8 GiB), written and read once per step (~2 % of the step time at the headline shape).  The N x M Gram is generated inside the
+32 GiB or 40 % of the free device memory), written and read once per step (~2 % of the step time at the headline shape).  The N x M Gram is generated inside the
 kernels from the points (default: nothing N x M in memory) or -- opt-in `gram_cache`, when N x M doubles fit (the reference
 keeps k(Z, X) for the whole run, orthonormal.py:36-41) -- computed once and streamed, which takes the exponent work off the
 FP64 pipe (+9 % at the headline shape for 8.2 GB).
@@ -28,7 +28,11 @@ import torch
 from . import _native as nat
 from . import ops
 
-DEFAULT_DC_BUDGET = 8 << 30
+# Bound on the Dc chunk, the only N-sized intermediate.  32 GiB holds the whole headline problem (N = 1M rows x J = 4096 particles
+# = 30.5 GiB) in ONE forward + ONE backward launch per step: measured 8056 -> 8089 -> 8113 particle-updates/s at 8 / 16 / 33 GiB
+# (4 / 2 / 1 chunks per step; tools/dc_budget_compare.sh) -- fewer launch tails, longer backward splits.  Clamped to 40 % of the free
+# device memory when the workspace is planned (a B200 has 180 GB).
+DEFAULT_DC_BUDGET = int(os.environ.get("PLS_B200_DC_BUDGET_GIB", "32")) << 30
 ROW_ALIGN = 128
 DEFAULT_GRAM_CACHE_BYTES = 24 << 30
 
@@ -83,6 +87,7 @@ class LangevinEngine:
         self.weights_fn = weights_fn  # fills W (M x J) from the particles; default W = V~ P (OrthonormalBasis)
         dev = xa.device
         self.dc_budget_bytes = int(dc_budget_bytes)
+        self.workspace: Optional[torch.Tensor] = None
         self._gram_code = nat.GRAM_CACHED if gram is not None else (nat.GRAM_STAGED if self._gram_staged and self.n > 0 else nat.GRAM_GENERATED)
         self._plan_workspace(with_cost=False)
         self._neq_cost: Optional[torch.Tensor] = None
@@ -95,6 +100,12 @@ class LangevinEngine:
         Gram staging chunk.  The tensors below are views into it (the piecewise entry points and the tests use them)."""
         ctx, dev = self.ctx, self.xa.device
         plan = nat.StepPlan()
+        if self.dc_budget_bytes >= DEFAULT_DC_BUDGET:  # the default (or more): never more than 40 % of what the device has free
+            free, _ = torch.cuda.mem_get_info(dev)
+            if self.workspace is not None:
+                free += self.workspace.numel() * 8  # re-planning (a cost region is being added): the old workspace is released below
+            self.dc_budget_bytes = max(min(self.dc_budget_bytes, int(0.4 * free)), 1 << 28)
+        self.workspace = None
         if ctx.lib.pls_step_plan_f64(ctx.handle, self.n, self.m, self.m_k, self.j, self.dc_budget_bytes, self._gram_code, int(with_cost),
                                      C.byref(plan)) != 0:
             raise ValueError(f"pls_step_plan_f64 rejected the shape N={self.n} M={self.m} M_k={self.m_k} J={self.j}")
