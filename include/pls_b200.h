@@ -250,7 +250,8 @@ int pls_flat_math_f64(pls_ctx* ctx, int op, const double* a, const double* b, in
  *   dc_budget_bytes  bound on the only N-sized intermediate, the Dc chunk (<= 0: 32 GiB -- the headline N = 1M x J = 4096 in one chunk);
  *   gram_mode        PLS_GRAM_GENERATED: Gram tiles regenerated inside the kernels, nothing N x M in memory (default path);
  *                    PLS_GRAM_STAGED:    k(X_c, Z) of the chunk in flight re-formed every step into a chunk-sized region of the
- *                                        workspace (pls_gram_fill_f64) and streamed by that chunk's two launches;
+ *                                        workspace (pls_gram_fill_f64) and streamed by that chunk's two launches (chunks are then
+ *                                        also bounded by 2 GiB of Gram values: 262 144 rows at M = 1024);
  *                    PLS_GRAM_CACHED:    the caller keeps k(X, Z) (pls_gram_f64 layout of the pls_*_cached_f64 calls) and passes it;
  *   with_cost        reserve room for the per-row-tile cost sums (needed when cost_sums / energy_out is requested).
  * The workspace is plan->workspace_bytes bytes of device memory, 256-byte aligned; after pls_grad_f64 the gradient

@@ -40,6 +40,11 @@ int pls_step_plan_f64(const pls_ctx* ctx, int64_t n, int64_t m, int64_t m_k, int
   plan->gram_mode = gram_mode;
   plan->with_cost = with_cost != 0;
   int64_t rows = (dc_budget_bytes / (plan->ldj * 8)) / ROW_ALIGN * ROW_ALIGN;
+  if (gram_mode == PLS_GRAM_STAGED) {
+    // the staging buffer must stay chunk-sized ("nothing N x M kept"): at most 2 GiB of Gram values per chunk
+    const int64_t staged_rows = ((2LL << 30) / (pls_gram_cache_ld(m) * 8)) / ROW_ALIGN * ROW_ALIGN;
+    if (rows > staged_rows) rows = staged_rows;
+  }
   if (rows < ROW_ALIGN) rows = ROW_ALIGN;
   plan->chunk_rows = n < rows ? n : rows;
   plan->n_chunks = plan->chunk_rows > 0 ? (int32_t)((n + plan->chunk_rows - 1) / plan->chunk_rows) : 0;
