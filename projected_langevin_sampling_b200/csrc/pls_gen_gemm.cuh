@@ -77,7 +77,28 @@ static __device__ __forceinline__ D4 cost_derivative4_as(const pls_cost& c, doub
   r.d = cost_derivative(cc, y, f.d, m);
   return r;
 }
+// `c->reserved` carries the case index cost_id * 8 + link_id * 2 + closed_form (set by the launcher): the two closed forms the
+// reference's experiments run at scale are tested for FIRST, before the cost struct is copied and the jump table is taken --
+// all inside this routine, so the kernels that call it are unchanged (a Poisson branch in the kernel's own epilogue cost the
+// Gaussian forward 0.9 %).
+constexpr int kCasePoissonSquareCF = PLS_COST_POISSON * 8 + PLS_LINK_SQUARE * 2 + 1;
+constexpr int kCaseBernoulliSigmoidCF = PLS_COST_BERNOULLI * 8 + PLS_LINK_SIGMOID * 2 + 1;
 static __device__ __noinline__ D4 cost_derivative4(const pls_cost* c, const double* exp_table, double y, D4 f) {
+  const int fast_case = c->reserved;
+  if (fast_case == kCasePoissonSquareCF) {  // -2 y / F + 2 F (poisson.py:68-82): no parameter of the struct is needed
+    const FlatMath m{exp_table};
+    D4 r;
+    r.a = -2.0 * m.div(y, f.a) + 2.0 * f.a;
+    r.b = -2.0 * m.div(y, f.b) + 2.0 * f.b;
+    r.c = -2.0 * m.div(y, f.c) + 2.0 * f.c;
+    r.d = -2.0 * m.div(y, f.d) + 2.0 * f.d;
+    return r;
+  }
+  if (fast_case == kCaseBernoulliSigmoidCF) {  // only the link's jitter is read
+    pls_cost cb;
+    cb.link_jitter = c->link_jitter;
+    return cost_derivative4_as<PLS_COST_BERNOULLI, PLS_LINK_SIGMOID, 1>(cb, y, f, exp_table);
+  }
   const pls_cost cc = *c;
 #define PLS_CASE(CID, LID)                                                   \
   case (CID * 8 + LID * 2 + 0): return cost_derivative4_as<CID, LID, 0>(cc, y, f, exp_table); \
@@ -955,6 +976,7 @@ cudaError_t launch_one(const pls_ctx* ctx, GenGemmParams p, cudaStream_t stream)
   if ((int64_t)smem > ctx->max_smem_optin) return cudaErrorInvalidConfiguration;
   p.wbuf_ok = 0;
   p.both = ctx->fused_functor;
+  p.cost.reserved = p.cost.cost_id * 8 + p.cost.link_id * 2 + (p.cost.closed_form != 0);  // case index for cost_derivative4's fast paths
   if (!BACKWARD && (int64_t)gen_gemm_smem_bytes_wbuf<RT>(p.sp) <= ctx->max_smem_optin) {
     if (gen_gemm_smem_bytes_wbuf<RT>(p.sp) > smem) smem = gen_gemm_smem_bytes_wbuf<RT>(p.sp);
     p.wbuf_ok = 1;
