@@ -165,6 +165,17 @@ static __device__ __forceinline__ D8 cost_both4_as(const pls_cost& c, double y, 
   return r;
 }
 static __device__ __noinline__ D8 cost_both4(const pls_cost* c, const double* exp_table, double y, D4 f) {
+  const int fast_case = c->reserved;  // as in cost_derivative4: the two closed forms run at scale skip the struct copy and the jump table
+  if (fast_case == kCasePoissonSquareCF) {
+    pls_cost cb;  // (no parameter is read)
+    cb.link_jitter = 0.0;
+    return cost_both4_as<PLS_COST_POISSON, PLS_LINK_SQUARE, 1>(cb, y, f, exp_table);
+  }
+  if (fast_case == kCaseBernoulliSigmoidCF) {
+    pls_cost cb;
+    cb.link_jitter = c->link_jitter;
+    return cost_both4_as<PLS_COST_BERNOULLI, PLS_LINK_SIGMOID, 1>(cb, y, f, exp_table);
+  }
   const pls_cost cc = *c;
 #define PLS_CASE(CID, LID)                                                   \
   case (CID * 8 + LID * 2 + 0): return cost_both4_as<CID, LID, 0>(cc, y, f, exp_table); \
