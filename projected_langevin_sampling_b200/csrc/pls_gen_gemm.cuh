@@ -30,12 +30,15 @@
 //   * the loop over 8-point groups is flat and branch-free (the Gram source is a template parameter) and the Gram values of
 //     a whole 32-point stage are produced one stage ahead, in two register sets that swap roles (never copied), so ptxas
 //     interleaves the 8 independent exponent chains of the NEXT stage with the DMMAs of the current one.
-//   * NS = 2 (default whenever the particle slice is an even number of 256-column tiles): the CTA tile is 64 x 512.  The 64
+//   * NS = 2 (default when the particle slice is an even number of 256-column tiles and the launch is large enough for the wider
+//     tile to pay -- choose_tile_ns, pls_internal.h): the CTA tile is 64 x 512.  The 64
 //     accumulators of the SECOND 256-column half are parked in tensor memory (tcgen05.st / tcgen05.ld, 2 x 128 columns per
 //     warp, ping-pong) and swapped with the register set once per 32-point chunk; the streamed blocks come in the order
 //     A0 B0 | B1 A1 | A2 B2 ... so a chunk costs ONE swap (137 clk, tools/tmem_swap_microbench.cu) and every generated Gram
 //     value feeds 512 columns: the exponent + exp share of the FP64 pipe halves (7.4 % -> 3.7 % at D = 8).  Each column is
-//     still accumulated over the chunks in order, so the results are bit-identical to NS = 1.
+//     still accumulated over the chunks in order, so the results are bit-identical to NS = 1.  The reduction points of chunk
+//     c + 1 travel with the SECOND block of chunk c (its Gram values are formed during that block), so no warp waits on a block
+//     ahead of the one it multiplies; the stage refill (one lane, while its warp waits) is free of divisions.
 //   * optional KSRC_CACHED variant (pls_*_cached_f64): the caller keeps k(X, Z) in HBM and the kernels LOAD their fragment
 //     values (L2::evict_last, one stage ahead) instead of generating them -- the FP64 pipe then runs nothing but the
 //     contraction.  The default path generates: nothing N x M is ever in memory.
