@@ -95,6 +95,7 @@ int pls_ctx_create(int device, pls_ctx** out) {
   if (const char* env = getenv("PLS_B200_TILE_RT")) c->tile_rt = atoi(env);
   if (const char* env = getenv("PLS_B200_TILE_NS")) c->tile_ns = atoi(env);
   if (const char* env = getenv("PLS_B200_FUSED_FUNCTOR")) c->fused_functor = atoi(env);
+  if (const char* env = getenv("PLS_B200_CLUSTER")) c->cluster = atoi(env);
   *out = c;
   return 0;
 }
@@ -158,7 +159,8 @@ int pls_backward_splits(const pls_ctx* ctx, int64_t n_rows, int64_t m, int64_t j
   // stages), and among the admissible counts the one that fills whole waves best (ties: fewer splits, less Gp traffic).
   const int sms = (ctx && ctx->sm_count > 0) ? ctx->sm_count : 148;
   const int rt = pls::choose_tile_rt(ctx, j);
-  const int64_t br = pls::tile_rows(rt), bj = pls::tile_cols(rt) * pls::choose_tile_ns(ctx, j, false, m, n_rows, true);  // (the generated-Gram default)
+  const int ns = pls::choose_tile_ns(ctx, j, false, m, n_rows, true);
+  const int64_t br = pls::tile_rows(rt), bj = pls::tile_cols(rt) * ns * (ns == 2 ? pls::choose_cluster(ctx, j) : 1);  // (the generated-Gram default)
   const int64_t tiles = ((m + br - 1) / br) * ((j + bj - 1) / bj);
   if (tiles <= 0 || n_rows <= 0) return 1;
   const int64_t chunks = (n_rows + pls::BK - 1) / pls::BK;

@@ -233,6 +233,45 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, in
 }
 constexpr int KSRC_LINEAR = 0, KSRC_RBF = 1, KSRC_CACHED = 2;
 
+// ---- thread-block cluster helpers (CL = 2: the two CTAs of a cluster share the generation of the Gram values) -------------------
+__device__ __forceinline__ unsigned cluster_ctarank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, unsigned rank) {  // shared::cta address -> shared::cluster address in `rank`
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+// two doubles into the peer's shared memory; completion is signalled as 16 transaction bytes on the peer's mbarrier
+__device__ __forceinline__ void st_async_v2(uint32_t remote_addr, double a, double b, uint32_t remote_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f64 [%0], {%1, %2}, [%3];" ::"r"(remote_addr), "d"(a), "d"(b),
+               "r"(remote_bar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t remote_bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote_bar) : "memory");  // (default semantics, as CUTLASS's ClusterBarrier::arrive)
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {  // acquire at cluster scope: data written by the peer CTA
+  const uint32_t addr = smem_u32(bar);
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "CWAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra CWAIT_DONE;\n"
+      "bra CWAIT_LOOP;\n"
+      "CWAIT_DONE:\n"
+      "}\n" ::"r"(addr),
+      "r"(parity)
+      : "memory");
+}
+
 // L2 eviction policies.  The persistent forward CTAs that share a Gram row slab (the 16 column tiles of a row tile) drift
 // apart by several tile times while 8.6 GB of Dc stream through L2 per launch: the cached Gram values are loaded evict_last and
 // Dc is stored evict_first so that the slab survives until its last reader (ncu: DRAM reads of a forward launch 9.9 -> see
@@ -280,13 +319,17 @@ __device__ __forceinline__ unsigned atom_add_shared(unsigned* addr, unsigned v) 
 // register budget; the backward role is instantiated with EPI = -1.
 // NS: 256-column accumulator sets per CTA tile (1, or 2 with the second set parked in tensor memory; RT = 1 and the
 // register epilogues only).
-template <int NKD, bool BACKWARD, int KSRC, int RT, int EPI, int NS>
+// CL: CTAs per cluster (1, or 2 with NS = 2: the two CTAs of a cluster work on adjacent 512-column tiles of the same rows and
+// reduction range; the Gram values of chunk c are formed by the CTA of rank c mod 2 only and mailed to its peer through distributed
+// shared memory, so every generated value feeds 1024 columns).
+template <int NKD, bool BACKWARD, int KSRC, int RT, int EPI, int NS, int CL = 1>
 __global__ void __launch_bounds__(NTHREADS, 1)
     gen_gemm_kernel(const GenGemmParams p, const __grid_constant__ CUtensorMap tm3, const __grid_constant__ CUtensorMap tm2) {
   using T = Tile<RT>;
   constexpr int NT = T::NT, BR = T::BR, BJ = T::BJ, NPR = T::NPR, STAGE_BYTES = T::STAGE_BYTES;
   constexpr int BJT = BJ * NS;  // columns of the CTA tile
   static_assert(NS == 1 || (NS == 2 && RT == 1 && KSRC != KSRC_CACHED), "accumulator parking: 64 x 512 tiles of generated Gram values");
+  static_assert(CL == 1 || (CL == 2 && NS == 2), "Gram sharing across a cluster builds on the 64 x 512 tile");
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);  // the swizzle needs 1024-byte stages
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);                      // [STAGES]
@@ -301,6 +344,9 @@ __global__ void __launch_bounds__(NTHREADS, 1)
   unsigned* tile_done = released + 4;                                          // [2] warps that published their sums, by tile parity
   volatile unsigned* combined = released + 6;                                  // tiles whose sums have been combined
   uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(smem_raw + 96);          // NS = 2: base address of the tensor-memory allocation
+  uint64_t* kfull = reinterpret_cast<uint64_t*>(smem_raw + 3072);              // CL = 2, [NWARPS]: the peer's Gram values have arrived in sK
+  uint64_t* kfree = kfull + NWARPS;                                            // CL = 2, [NWARPS]: the peer has read the values I mailed
+  double* sK = sC + 2 * NTHREADS;                                              // CL = 2, [NWARPS][32 lanes][8]: mailbox for the peer's Gram values
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -316,16 +362,18 @@ __global__ void __launch_bounds__(NTHREADS, 1)
   //   fastest: the CTAs in flight share training rows and the whole W).  The copy pipeline runs across tile boundaries (the
   //   first stages of the next tile land during the epilogue of the current one) and nothing is re-initialised per tile.
   const int64_t n_row_tiles = (p.n_rows + BR - 1) / BR;
-  const int64_t n_col_tiles = (p.j + BJT - 1) / BJT;
+  const int64_t n_col_tiles = (p.j + BJT * CL - 1) / (BJT * CL);  // tiles of a CLUSTER: CL adjacent CTA tiles
   const int64_t total_tiles = n_row_tiles * n_col_tiles * (BACKWARD ? p.splits : 1);
-  const int my_tiles = BACKWARD ? 1 : (int)((total_tiles - (int64_t)blockIdx.x + gridDim.x - 1) / gridDim.x);
+  const unsigned crank = (CL == 2) ? cluster_ctarank() : 0u;      // this CTA's column position inside its cluster's tile
+  const unsigned cid = blockIdx.x / CL, ncl = gridDim.x / CL;     // cluster index / clusters in the grid
+  const int my_tiles = BACKWARD ? 1 : (int)((total_tiles - (int64_t)cid + ncl - 1) / ncl);
 
   // reduction range: the forward role reduces over all inducing points in every tile; the backward role over its split
   int64_t begin = 0, end = p.red_total;
   int64_t bw_rt = 0, bw_ct = 0;
   int split = 0;
   if (BACKWARD) {
-    int64_t bid = blockIdx.x;
+    int64_t bid = cid;
     bw_rt = bid % n_row_tiles;
     bid /= n_row_tiles;
     bw_ct = bid % n_col_tiles;
@@ -349,7 +397,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
       rt = bw_rt;
       ct = bw_ct;
     } else {
-      const unsigned tile = blockIdx.x + (unsigned)ti * gridDim.x;
+      const unsigned tile = cid + (unsigned)ti * ncl;
       const unsigned q = tile / nct32;
       ct = (int64_t)(tile - q * nct32);
       rt = (int64_t)q;
@@ -367,12 +415,22 @@ __global__ void __launch_bounds__(NTHREADS, 1)
       released[s] = 0;
     }
     released[4] = released[5] = released[6] = 0;
+    if (CL == 2)
+      for (int w = 0; w < NWARPS; ++w) {
+        mbar_init(&kfull[w], 1);
+        mbar_init(&kfree[w], 1);
+      }
     fence_mbar_init();
   }
   if (NS == 2 && warp == 0) tmem_alloc_512(tmem_base_s);  // all 512 columns: 2 warps per lane quarter x 2 slots x 128 columns
   fence_proxy_async();  // generic-proxy zero fill ordered before the async-proxy bulk copies
   if (NS == 2) tmem_fence_before_sync();
   __syncthreads();
+  int nrecv = 0, nsent = 0;  // CL = 2: chunks whose Gram values this warp has received from / mailed to its peer
+  if (CL == 2) {
+    if (lane == 0) mbar_expect_tx(&kfull[warp], 32u * 64u);  // armed for the first delivery: 8 doubles from each of the peer warp's lanes
+    cluster_sync_all();  // both CTAs' barriers exist and are armed before anything is mailed
+  }
   uint32_t tslot = 0;  // this warp's two parking slots: tslot, tslot + 128 (its own 32 lanes, 256 of the 512 columns)
   if (NS == 2) {
     tmem_fence_after_sync();
@@ -392,7 +450,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     const int half = (NS == 2) ? (((c & 1) != 0) != ((b & 1) != 0) ? 1 : 0) : 0;
     const int cp = (NS == 2) ? ((b == 0) ? 0 : ((b & 1) ? c + 1 : nchunks)) : c;  // chunk whose points travel with this block
     const bool with_points = KSRC != KSRC_CACHED && cp < nchunks;
-    const int64_t j0 = (int64_t)ct_i * BJT + half * BJ;
+    const int64_t j0 = ((int64_t)ct_i * CL + crank) * BJT + half * BJ;
     const bool use3d = p.tma3d && (j0 + BJ <= p.full_blocks * 16 || p.full_blocks * 16 == p.ldb);
     const int64_t k0 = begin + (int64_t)c * BK;
     const int64_t kp0 = begin + (int64_t)cp * BK;
@@ -418,7 +476,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
   // refill of the stage a warp has just released with the block STAGES further on: same stage; the block belongs to the tile the
   // warp is in (column position ct_cur) or to this CTA's next tile, gridDim.x tiles further on -- no division on this path, which
   // one lane runs while the rest of its warp waits
-  const int gstep = BACKWARD ? 0 : (int)(gridDim.x % nct32);
+  const int gstep = BACKWARD ? 0 : (int)(ncl % nct32);
   auto issue_from = [&](int gc_cur, int ct_cur, int b_cur, int stage) {
     int b = b_cur + STAGES, ct_i = ct_cur;
     if (b >= nblocks) {
@@ -606,9 +664,35 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     // DMMAs of the following block, a whole block of tensor work later, so the load latency hides behind it.  (With a
     // kc = kn copy ptxas hoists each move to right after the last DMMA that reads its target, ~30 DMMAs after the load.)
     double kA[LA][2][RT], kB[LA][2][RT];
+    // CL = 2: the Gram values of chunk c are formed by the CTA of rank c mod 2 and mailed to the same warp and lane of the peer CTA
+    // (the two CTAs hold the same rows and reduction range, so the fragment layouts coincide): 4 x 16 bytes per lane through
+    // st.async, completion counted as transaction bytes on the peer's kfull barrier; the peer reads its mailbox at the start of the
+    // chunk, re-arms the barrier and, once the values have been consumed, releases the mailbox with an arrive on my kfree barrier.
+    auto mail_k = [&](const double (&k)[LA][2][RT]) {
+      if (nsent > 0) mbar_wait_cluster(&kfree[warp], (uint32_t)((nsent - 1) & 1));  // the peer has read what I mailed last
+      const uint32_t rbox = map_to_cta(smem_u32(sK + (warp * 32 + lane) * 8), crank ^ 1u);
+      const uint32_t rbar = map_to_cta(smem_u32(&kfull[warp]), crank ^ 1u);
+#pragma unroll
+      for (int q = 0; q < LA; ++q) st_async_v2(rbox + 16u * q, k[q][0][0], k[q][1][0], rbar);
+      ++nsent;
+    };
+    auto receive_k = [&](double (&k)[LA][2][RT]) {
+      mbar_wait_cluster(&kfull[warp], (uint32_t)(nrecv & 1));
+      const double2* box = reinterpret_cast<const double2*>(sK + (warp * 32 + lane) * 8);
+#pragma unroll
+      for (int q = 0; q < LA; ++q) {
+        const double2 v = box[q];
+        k[q][0][0] = v.x;
+        k[q][1][0] = v.y;
+      }
+      ++nrecv;
+    };
     if (nchunks > 0) {
       mbar_wait(&full[stage], phase);
-      gram_block(sP + stage * BK * sp, 0, 2 * t, kA);
+      if (CL == 1 || crank == 0u) {
+        gram_block(sP + stage * BK * sp, 0, 2 * t, kA);
+        if constexpr (CL == 2) mail_k(kA);
+      }
     }
     // One chunk = one 32-point stage = 4 groups, fully unrolled (264 DMMAs).  The next stage was issued two chunk times ago;
     // its Gram values (same tile only: they depend on the tile's rows) are formed before this stage's last block of DMMAs.
@@ -664,8 +748,14 @@ __global__ void __launch_bounds__(NTHREADS, 1)
         mma_step(bgrp + off1, k[q][1]);
       }
     };
-    auto release_block = [&](int b_cur) {  // as in run_chunk: the last warp to release a stage refills it (no deferral: register epilogues only)
+    auto release_block = [&](int b_cur, bool free_mailbox) {  // as in run_chunk: the last warp to release a stage refills it (no deferral: register epilogues only)
       __syncwarp();
+      if (CL == 2 && free_mailbox && lane == 0) {
+        // every lane's mailbox values have been consumed by the block's DMMAs: re-arm my barrier for the next delivery, then tell
+        // the peer that its next one may come
+        mbar_expect_tx(&kfull[warp], 32u * 64u);
+        mbar_arrive_remote(map_to_cta(smem_u32(&kfree[warp]), crank ^ 1u));
+      }
       if (lane == 0) {
         if (atom_add_shared(&released[stage], 1u) == NWARPS - 1) {
           released[stage] = 0;
@@ -678,8 +768,12 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     };
     auto run_pair = [&](int c, double (&k0)[LA][2][RT], double (&k1)[LA][2][RT]) {
       if (c > 0) mbar_wait(&full[stage], phase);  // (chunk 0: the tile prologue waited for this block, which carries its points)
+      const bool mine = CL == 1 || (unsigned)(c & 1) == crank;  // this chunk's Gram values were formed here (else: mailed by the peer)
+      if constexpr (CL == 2) {
+        if (!mine) receive_k(k0);
+      }
       dmma_block(k0);
-      release_block(2 * c);
+      release_block(2 * c, !mine);
       // park the finished half's accumulators, fetch the other half's (zero before its first block)
       if constexpr (NS == 2) {
         tmem_store64(tslot + (unsigned)(c & 1) * 128u, acc[0]);
@@ -695,9 +789,12 @@ __global__ void __launch_bounds__(NTHREADS, 1)
         }
       }
       mbar_wait(&full[stage], phase);
-      if (c + 1 < nchunks) gram_block(sP + stage * BK * sp, 0, (c + 1) * BK + 2 * t, k1);  // the next chunk's points came with this block
+      if (c + 1 < nchunks && (CL == 1 || !mine)) {  // (CL = 2: the next chunk is mine exactly when this one was not)
+        gram_block(sP + stage * BK * sp, 0, (c + 1) * BK + 2 * t, k1);  // the next chunk's points came with this block
+        if constexpr (CL == 2) mail_k(k1);
+      }
       dmma_block(k0);
-      release_block(2 * c + 1);
+      release_block(2 * c + 1, false);
     };
 #pragma unroll 1
     for (int c = 0; c < nchunks;) {
@@ -732,7 +829,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
       half = (eh == 0) ? hreg : 1 - hreg;
       if (eh == 1 && nchunks > 0) tmem_load64(tslot + (unsigned)((nchunks - 1) & 1) * 128u, acc[0]);
     }
-    const int64_t j0 = ct * BJT + half * BJ;
+    const int64_t j0 = (ct * CL + crank) * BJT + half * BJ;
     const int vt = ti * NS + eh;
     if (BACKWARD) {
 #pragma unroll
@@ -964,6 +1061,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     if (ti + 1 < my_tiles) load_rows(next_row0, a2, crow);
     }  // halves
   }
+  if (CL == 2) cluster_sync_all();  // no CTA leaves while its peer may still mail into its shared memory or arrive on its barriers
   if (NS == 2) {  // every warp has drained its parking slots: release the tensor memory
     tmem_fence_before_sync();
     __syncthreads();
@@ -971,27 +1069,30 @@ __global__ void __launch_bounds__(NTHREADS, 1)
   }
 }
 
-template <int NKD, bool BACKWARD, int KSRC, int RT, int EPI, int NS = 1>
+template <int NKD, bool BACKWARD, int KSRC, int RT, int EPI, int NS = 1, int CL = 1>
 cudaError_t launch_one(const pls_ctx* ctx, GenGemmParams p, cudaStream_t stream) {
   using T = Tile<RT>;
   if (KSRC == KSRC_CACHED) p.sp = 0;  // no point rows are staged
-  int64_t grid = ((p.n_rows + T::BR - 1) / T::BR) * ((p.j + T::BJ * NS - 1) / (T::BJ * NS));
+  // tiles of a cluster (CL adjacent CTA tiles); the grid counts clusters until the end of this block
+  int64_t grid = ((p.n_rows + T::BR - 1) / T::BR) * ((p.j + T::BJ * NS * CL - 1) / (T::BJ * NS * CL));
   if (BACKWARD) grid *= p.splits;
   else {
     const int64_t tiles = grid;
-    if (grid > ctx->sm_count) grid = ctx->sm_count;  // persistent forward: one CTA per SM walks the tiles
+    if (grid > ctx->sm_count / CL) grid = ctx->sm_count / CL;  // persistent forward: one CTA per SM walks the tiles
     // the kernel counts the chunks a CTA streams over all its tiles in 32 bits
     if (grid > 0 && ((tiles + grid - 1) / grid) * ((p.red_total + BK - 1) / BK) * NS > 2147483647LL) return cudaErrorInvalidConfiguration;
     if (tiles + grid > 2147483647LL) return cudaErrorInvalidConfiguration;  // the kernel numbers its tiles in 32 bits
   }
   if (grid <= 0 || p.red_total <= 0) return cudaSuccess;
+  grid *= CL;
   if (grid > 2147483647LL) return cudaErrorInvalidConfiguration;
-  size_t smem = gen_gemm_smem_bytes<RT>(p.sp);
+  size_t smem = gen_gemm_smem_bytes<RT>(p.sp) + (CL == 2 ? sizeof(double) * NTHREADS * 8 : 0);  // + the Gram mailbox
   if ((int64_t)smem > ctx->max_smem_optin) return cudaErrorInvalidConfiguration;
   p.wbuf_ok = 0;
+  if (CL == 2 && !BACKWARD && (EPI == PLS_EPI_COST || EPI == PLS_EPI_COST_DERIVATIVE_AND_COST)) return cudaErrorInvalidConfiguration;  // (no room for the per-warp sums)
   p.both = ctx->fused_functor;
   p.cost.reserved = p.cost.cost_id * 8 + p.cost.link_id * 2 + (p.cost.closed_form != 0);  // case index for cost_derivative4's fast paths
-  if (!BACKWARD && (int64_t)gen_gemm_smem_bytes_wbuf<RT>(p.sp) <= ctx->max_smem_optin) {
+  if (CL == 1 && !BACKWARD && (int64_t)gen_gemm_smem_bytes_wbuf<RT>(p.sp) <= ctx->max_smem_optin) {
     if (gen_gemm_smem_bytes_wbuf<RT>(p.sp) > smem) smem = gen_gemm_smem_bytes_wbuf<RT>(p.sp);
     p.wbuf_ok = 1;
   }
@@ -999,10 +1100,26 @@ cudaError_t launch_one(const pls_ctx* ctx, GenGemmParams p, cudaStream_t stream)
   cudaError_t e = make_stream_maps(ctx, p.b, p.red_total, p.ldb, T::NPR, &tm3, &tm2, &p.tma3d);
   if (e != cudaSuccess) return e;
   p.full_blocks = p.ldb / 16;
-  e = cudaFuncSetAttribute(gen_gemm_kernel<NKD, BACKWARD, KSRC, RT, EPI, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  e = cudaFuncSetAttribute(gen_gemm_kernel<NKD, BACKWARD, KSRC, RT, EPI, NS, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  gen_gemm_kernel<NKD, BACKWARD, KSRC, RT, EPI, NS><<<(unsigned)grid, NTHREADS, smem, stream>>>(p, tm3, tm2);
-  return cudaGetLastError();
+  if constexpr (CL == 1) {
+    gen_gemm_kernel<NKD, BACKWARD, KSRC, RT, EPI, NS, CL><<<(unsigned)grid, NTHREADS, smem, stream>>>(p, tm3, tm2);
+    return cudaGetLastError();
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid, 1, 1);
+    cfg.blockDim = dim3(NTHREADS, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, gen_gemm_kernel<NKD, BACKWARD, KSRC, RT, EPI, NS, CL>, p, tm3, tm2);
+  }
 }
 
 // ROLE: -1 = backward, otherwise the forward epilogue PLS_EPI_*
@@ -1022,6 +1139,12 @@ cudaError_t launch_role(const pls_ctx* ctx, const GenGemmParams& p, cudaStream_t
   if (rbf && p.rt == 1 && choose_tile_ns(ctx, p.j, false, p.n_rows, p.red_total, BW) == 2) {
     const bool sums = ROLE == PLS_EPI_COST || ROLE == PLS_EPI_COST_DERIVATIVE_AND_COST;
     const bool sums_from_registers = (int64_t)gen_gemm_smem_bytes_wbuf<1>(p.sp) <= ctx->max_smem_optin && 2 * ((p.red_total + BK - 1) / BK) > STAGES;
+    // ... and, for the roles without cost sums, pairs of CTAs that share the generation of the Gram values (CL = 2): needs whole
+    // 1024-column cluster tiles and room for the mailbox
+    if constexpr (ROLE < 0 || ROLE == PLS_EPI_PREDICTION || ROLE == PLS_EPI_COST_DERIVATIVE) {
+      if (choose_cluster(ctx, p.j) == 2 && (int64_t)(gen_gemm_smem_bytes<1>(p.sp) + sizeof(double) * NTHREADS * 8) <= ctx->max_smem_optin)
+        return launch_one<NKD, BW, KSRC_RBF, 1, ROLE, 2, 2>(ctx, p, stream);
+    }
     if (!sums || sums_from_registers) return launch_one<NKD, BW, KSRC_RBF, 1, ROLE, 2>(ctx, p, stream);
   }
   if (p.rt == 1) return rbf ? launch_one<NKD, BW, KSRC_RBF, 1, ROLE>(ctx, p, stream) : launch_one<NKD, BW, KSRC_LINEAR, 1, ROLE>(ctx, p, stream);
