@@ -160,7 +160,7 @@ int pls_backward_splits(const pls_ctx* ctx, int64_t n_rows, int64_t m, int64_t j
   const int sms = (ctx && ctx->sm_count > 0) ? ctx->sm_count : 148;
   const int rt = pls::choose_tile_rt(ctx, j);
   const int ns = pls::choose_tile_ns(ctx, j, false, m, n_rows, true);
-  const int64_t br = pls::tile_rows(rt), bj = pls::tile_cols(rt) * ns * (ns == 2 ? pls::choose_cluster(ctx, j) : 1);  // (the generated-Gram default)
+  const int64_t br = pls::tile_rows(rt), bj = pls::tile_cols(rt) * ns * (ns == 2 ? pls::choose_cluster(ctx, j, m, n_rows, true) : 1);  // (the generated-Gram default)
   const int64_t tiles = ((m + br - 1) / br) * ((j + bj - 1) / bj);
   if (tiles <= 0 || n_rows <= 0) return 1;
   const int64_t chunks = (n_rows + pls::BK - 1) / pls::BK;

@@ -1142,7 +1142,8 @@ cudaError_t launch_role(const pls_ctx* ctx, const GenGemmParams& p, cudaStream_t
     // ... and, for the roles without cost sums, pairs of CTAs that share the generation of the Gram values (CL = 2): needs whole
     // 1024-column cluster tiles and room for the mailbox
     if constexpr (ROLE < 0 || ROLE == PLS_EPI_PREDICTION || ROLE == PLS_EPI_COST_DERIVATIVE) {
-      if (choose_cluster(ctx, p.j) == 2 && (int64_t)(gen_gemm_smem_bytes<1>(p.sp) + sizeof(double) * NTHREADS * 8) <= ctx->max_smem_optin)
+      if (choose_cluster(ctx, p.j, p.n_rows, p.red_total, BW) == 2 &&
+          (int64_t)(gen_gemm_smem_bytes<1>(p.sp) + sizeof(double) * NTHREADS * 8) <= ctx->max_smem_optin)
         return launch_one<NKD, BW, KSRC_RBF, 1, ROLE, 2, 2>(ctx, p, stream);
     }
     if (!sums || sums_from_registers) return launch_one<NKD, BW, KSRC_RBF, 1, ROLE, 2>(ctx, p, stream);

@@ -17,7 +17,7 @@ struct pls_ctx {
   const uint64_t* step_counter = nullptr;  // device counter added to pls_project_update_f64's `step` (pls_set_step_counter)
   int tile_rt = 0;  // 0 = choose per launch from the particle count; 1 / 2 force a tile shape (PLS_B200_TILE_RT, tests)
   int fused_functor = 1;  // fused training epilogue: one call for cost values + derivatives (0: two calls; PLS_B200_FUSED_FUNCTOR, A/B runs)
-  int cluster = 0;  // 0 / 1 = one CTA per tile; 2 = pairs of CTAs share the Gram generation when the shape allows (PLS_B200_CLUSTER; experimental)
+  int cluster = 0;  // pairs of CTAs sharing the Gram generation: 0 = rule of choose_cluster (backward role only), 1 = never, 2 = both roles (PLS_B200_CLUSTER)
   int tile_ns = 0;  // 0 = park a second accumulator set in tensor memory whenever the shape allows; 1 = never (PLS_B200_TILE_NS, tests)
   std::string error;
   // pls_profile_begin / pls_profile_end: CUDA-event pairs around every launch of the hot kernel (role 0 forward, 1 backward)
@@ -86,10 +86,19 @@ inline int choose_tile_ns(const pls_ctx* ctx, int64_t j, bool cached, int64_t ou
   return (tiles * max_splits >= 8 * sms) ? 2 : 1;
 }
 
-// CTAs per cluster of the generated-Gram kernels (on top of NS = 2): 2 when requested and the particle slice is a whole number of
-// 1024-column cluster tiles.
-inline int choose_cluster(const pls_ctx* ctx, int64_t j) {
-  return (ctx && ctx->cluster == 2 && ((j + 255) / 256) % 4 == 0) ? 2 : 1;
+// CTAs per cluster of the generated-Gram kernels (on top of NS = 2): 2 = pairs of CTAs on adjacent 512-column tiles share the
+// generation of the Gram values through distributed shared memory.  Needs a whole number of 1024-column cluster tiles.  Measured at
+// C4 (tools/cluster_compare.sh): backward 33.62 -> 33.83 TFLOP/s, persistent forward 32.73 -> 32.47 (tying warp w of one CTA to warp
+// w of its peer costs the forward the free drift of its epilogues), so the default rule (ctx->cluster == 0) pairs the BACKWARD
+// role only, and only when there are enough cluster tiles x splits for 8 waves; 1 = never, 2 = both roles whenever possible.
+inline int choose_cluster(const pls_ctx* ctx, int64_t j, int64_t out_rows, int64_t red_len, bool backward) {
+  if (!ctx || ctx->cluster == 1 || ((j + 255) / 256) % 4 != 0) return 1;
+  if (ctx->cluster == 2) return 2;
+  if (!backward) return 1;
+  const int64_t sms = ctx->sm_count > 0 ? ctx->sm_count : 148;
+  const int64_t chunks = (red_len + 31) / 32;
+  const int64_t max_splits = chunks / 8 > 1 ? chunks / 8 : 1;
+  return (((out_rows + 63) / 64) * ((j + 1023) / 1024) * max_splits >= 8 * sms) ? 2 : 1;
 }
 
 // Tensor maps of the streamed matrix b (rows x ldb doubles, 16-byte aligned, ldb even) for the hot kernel's stages of 32 rows
