@@ -48,7 +48,7 @@ for line in res.splitlines():
         fn = None
 names = demangle(list(counts))
 print(f"# {os.path.relpath(lib, ROOT)}: {len(counts)} kernels / device functions; archs: {sorted(set(arch.values()))}")
-print("# gen_gemm_kernel<NKD, BACKWARD, KSRC (0 linear, 1 RBF generated, 2 cached Gram), RT, EPI (-1 backward), NS (2 = second accumulator set parked in tensor memory)>")
+print("# gen_gemm_kernel<NKD, BACKWARD, KSRC (0 linear, 1 RBF generated, 2 cached Gram), RT, EPI (-1 backward), NS (2 = second accumulator set parked in tensor memory), CL (2 = CTA pairs sharing the Gram generation over DSMEM)>")
 print(f"# {'REG':>4s} {'STACK':>5s} {'instr':>7s} " + " ".join(f"{o:>7s}" for o in OPS) + "  kernel")
 tot = collections.Counter()
 for f, c in counts.items():
