@@ -114,6 +114,10 @@ void pls_set_tile_shape(pls_ctx* ctx, int rt);
  * ns = 1 never does; ns = 2 does whenever the shape allows it.  Results are bit-identical either way (each column is accumulated
  * in the same order).  Benchmarks and tests only; the environment variable PLS_B200_TILE_NS does the same. */
 void pls_set_tile_sets(pls_ctx* ctx, int ns);
+/* pairs of CTAs (a thread-block cluster of 2) on adjacent 512-column tiles sharing the generated Gram values through distributed
+ * shared memory: mode = 0 (default) the backward role when the launch is large enough, 1 never, 2 both roles whenever the particle
+ * slice is a whole number of 1024-column tiles.  Bit-identical results.  Environment: PLS_B200_CLUSTER. */
+void pls_set_tile_cluster(pls_ctx* ctx, int mode);
 
 /* ---- one-time setup ------------------------------------------------------------------------------------------ */
 /* Builds the augmented layout of a point set.  x: n x d (ldx).  inv_lengthscale, centre: HOST arrays of d doubles

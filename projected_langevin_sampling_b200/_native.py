@@ -79,6 +79,7 @@ SIGNATURES = {
     "pls_forward_tile_rows": (_int, [_vp, _i64]),
     "pls_set_tile_shape": (None, [_vp, _int]),
     "pls_set_tile_sets": (None, [_vp, _int]),
+    "pls_set_tile_cluster": (None, [_vp, _int]),
     "pls_backward_splits": (_int, [_vp, _i64, _i64, _i64]),
     "pls_prepare_points_f64": (_int, [_vp, _int, _vp, _i64, _int, _i64, C.POINTER(_dbl), C.POINTER(_dbl), _dbl, _vp, _vp]),
     "pls_gram_f64": (_int, [_vp, _int, _vp, _i64, _vp, _i64, _int, _vp, _i64, _vp]),

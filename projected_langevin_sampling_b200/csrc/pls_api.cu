@@ -197,6 +197,10 @@ void pls_set_tile_sets(pls_ctx* ctx, int ns) {
   if (ctx) ctx->tile_ns = (ns == 1 || ns == 2) ? ns : 0;
 }
 
+void pls_set_tile_cluster(pls_ctx* ctx, int mode) {
+  if (ctx) ctx->cluster = (mode == 1 || mode == 2) ? mode : 0;
+}
+
 int pls_prepare_points_f64(pls_ctx* ctx, int kernel_id, const double* x, int64_t n, int d, int64_t ldx,
                            const double* inv_lengthscale, const double* centre, double c_extra, double* out, void* stream) {
   if (!ctx) return 1;

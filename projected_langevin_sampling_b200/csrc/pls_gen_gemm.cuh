@@ -39,6 +39,11 @@
 //     still accumulated over the chunks in order, so the results are bit-identical to NS = 1.  The reduction points of chunk
 //     c + 1 travel with the SECOND block of chunk c (its Gram values are formed during that block), so no warp waits on a block
 //     ahead of the one it multiplies; the stage refill (one lane, while its warp waits) is free of divisions.
+//   * CL = 2 (backward role by default, choose_cluster in pls_internal.h): a cluster of two CTAs takes two adjacent 512-column tiles
+//     of the same rows and reduction range; the Gram values of chunk c are formed by the CTA of rank c mod 2 only and mailed lane to
+//     lane to the same warp of its peer through distributed shared memory (st.async + mbarrier transaction bytes; a remote arrive
+//     hands the mailbox back), so one generated value feeds 1024 columns.  Same bits; backward +0.6 %, the persistent forward -0.8 %
+//     (its warps lose the free drift of their epilogues), hence backward only.
 //   * optional KSRC_CACHED variant (pls_*_cached_f64): the caller keeps k(X, Z) in HBM and the kernels LOAD their fragment
 //     values (L2::evict_last, one stage ahead) instead of generating them -- the FP64 pipe then runs nothing but the
 //     contraction.  The default path generates: nothing N x M is ever in memory.

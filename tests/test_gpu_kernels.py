@@ -453,9 +453,18 @@ def test_parked_accumulators_are_bit_identical(ctx, n, m, d, j, ld, cost_name):
         ctx.lib.pls_set_tile_sets(ctx.handle, 1)  # never
         want = run_all()
         ctx.lib.pls_set_tile_sets(ctx.handle, 2)  # whenever the shape allows (the default rule would skip these small launches)
+        ctx.lib.pls_set_tile_cluster(ctx.handle, 1)
         got = run_all()
+        # ... and with pairs of CTAs sharing the generated Gram values through distributed shared memory (1024-column cluster tiles:
+        # J = 900, 1024 and 2048 here; the cost-sum epilogues and the other widths keep the single-CTA kernel)
+        ctx.lib.pls_set_tile_cluster(ctx.handle, 2)
+        paired = run_all()
     finally:
         ctx.lib.pls_set_tile_sets(ctx.handle, 0)
+        ctx.lib.pls_set_tile_cluster(ctx.handle, 0)
+    for name in got:
+        same = (paired[name] == got[name]) | (torch.isnan(paired[name]) & torch.isnan(got[name]))
+        assert bool(same.all()), f"{name}: {int((~same).sum())} entries differ between CTA pairs (CL = 2) and single CTAs"
     k_xz = ops.gram(ctx, nat.KERNEL_RBF, xa, za, d)
     ref_f = k_xz @ w[:, :j]
     assert (want["f"][:, :j] - ref_f).abs().max().item() < 1e-12 * max(1.0, ref_f.abs().max().item())
