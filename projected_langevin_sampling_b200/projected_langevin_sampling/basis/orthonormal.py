@@ -6,7 +6,6 @@ k(X, Z) regenerates its tiles inside the CUDA kernels (csrc/pls_gen_gemm.cuh).
 """
 from __future__ import annotations
 
-import math
 from typing import Dict, Optional, Tuple
 
 import torch
