@@ -275,3 +275,26 @@ def test_gaussian_predict_is_a_light_diagonal_normal():
     lo, hi = d.confidence_region()
     assert torch.equal(lo, torch.tensor([-1.0, 2.0], dtype=torch.float64)) and torch.equal(hi, torch.tensor([7.0, 2.0], dtype=torch.float64))
     assert torch.equal(d.covariance_matrix, torch.diag(d.variance)) and d.sample().shape == (2,)
+
+
+def test_bench_strong_scaling_placement_and_shared_config():
+    """bench.py at N GPUs: the named J = 4096 is split over a 1 x N grid (strong scaling, equal even slices that tile the
+    particle axis), and both arms print the same `config` dictionary for the same workload and world size."""
+    sys.path.insert(0, ROOT)
+    import bench
+    from projected_langevin_sampling_b200.distributed import GridPlacement
+
+    w = bench.WORKLOADS["c4"]
+    for world in (1, 2, 4, 8):
+        slices = [GridPlacement(rank=r, world=world, n_groups=1, j_groups=world).particles(w["j"]) for r in range(world)]
+        assert slices[0][0] == 0 and slices[-1][1] == w["j"]
+        assert all(a[1] == b[0] for a, b in zip(slices[:-1], slices[1:]))
+        assert {b - a for a, b in slices} == {w["j"] // world}
+        rows = [GridPlacement(rank=r, world=world, n_groups=1, j_groups=world).rows(w["n"]) for r in range(world)]
+        assert all(r == (0, w["n"]) for r in rows)  # data replicated: no row sharding in the default grid
+    cfg = bench.base_config(w, 8, "1x8")
+    assert cfg == bench.base_config(dict(w), 8, "1x8") and cfg["J_global"] == 4096 and cfg["N"] == 1_000_000 and cfg["M"] == 1024
+    # a 2 x 4 grid: rows split in two 128-aligned halves, particles in four slices; ranks of a row group share their particle slice
+    g = [GridPlacement(rank=r, world=8, n_groups=2, j_groups=4) for r in range(8)]
+    assert g[0].rows(w["n"])[1] == g[4].rows(w["n"])[0] and g[0].rows(w["n"])[1] % 128 == 0
+    assert g[1].particles(w["j"]) == g[5].particles(w["j"]) == (1024, 2048) and g[1].row_group_ranks() == [1, 5]
